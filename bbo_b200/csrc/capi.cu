@@ -1,0 +1,222 @@
+// extern "C" surface of libbbo_b200.so (see include/bbo_b200.h for the contract).
+#include <string>
+
+#include "fit.cuh"
+#include "score.cuh"
+
+namespace bbo {
+static thread_local std::string g_last_error;
+int cuda_fail(cudaError_t e, const char* what) {
+  g_last_error = std::string(cudaGetErrorName(e)) + ": " + cudaGetErrorString(e) + " at " + what;
+  return BBO_ERR_CUDA;
+}
+static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+static bool hyper_ok(const bbo_gp_hyper* h) {
+  return h != nullptr && h->d >= 1 && (h->kind == BBO_KERNEL_RBF || h->kind == BBO_KERNEL_MATERN52) &&
+         h->noise >= 0.0;
+}
+}  // namespace bbo
+
+using namespace bbo;
+
+extern "C" {
+
+int bbo_version(void) { return 100; }
+const char* bbo_last_cuda_error(void) { return g_last_error.c_str(); }
+int64_t bbo_padded_n(int64_t n) { return padded(n); }
+
+size_t bbo_gp_fit_workspace_bytes(int64_t n, int64_t d, int64_t batch) {
+  if (n < 1 || d < 1 || batch < 1) return 0;
+  return FitWorkspace::bytes(n, d, batch);
+}
+size_t bbo_gp_score_workspace_bytes(int64_t n, int64_t d, int64_t q_chunk, int32_t precision) {
+  if (n < 1 || d < 1 || q_chunk < 1) return 0;
+  return ScoreWorkspace::bytes(n, d, q_chunk, precision, false);
+}
+size_t bbo_gp_predict_workspace_bytes(int64_t n, int64_t d, int64_t q_chunk, int32_t want_full) {
+  if (n < 1 || d < 1 || q_chunk < 1) return 0;
+  return ScoreWorkspace::bytes(n, d, q_chunk, BBO_PREC_FP64, want_full != 0);
+}
+
+int bbo_cov_matrix(const bbo_gp_hyper* h, const double* hyp_dev, const double* X1_dev, int64_t q,
+                   const double* X2_dev, int64_t n, double* out_dev, int64_t ldo, void* stream) {
+  if (!hyper_ok(h) || q < 0 || n < 0 || ldo < n) return BBO_ERR_BAD_SHAPE;
+  if (!hyp_dev || !X1_dev || !X2_dev || !out_dev) return BBO_ERR_BAD_ARG;
+  return cov_matrix(*h, hyp_dev, X1_dev, q, X2_dev, n, out_dev, ldo, 0.0, S(stream));
+}
+
+int bbo_gp_fit_value_grad(const bbo_gp_hyper* h, int64_t n, int64_t batch, const double* X_dev,
+                          const double* y_dev, const double* hyp_dev, double* value_dev, double* grad_dev,
+                          int32_t* info_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  if (!hyper_ok(h) || n < 1 || batch < 1) return BBO_ERR_BAD_SHAPE;
+  if (!X_dev || !y_dev || !hyp_dev || !value_dev || !grad_dev || !info_dev) return BBO_ERR_BAD_ARG;
+  FitWorkspace w;
+  int rc = w.bind(workspace_dev, workspace_bytes, n, h->d, batch);
+  if (rc != BBO_OK) return rc;
+  return fit_value_grad(*h, w, X_dev, y_dev, hyp_dev, value_dev, grad_dev, info_dev, S(stream));
+}
+
+int bbo_gp_fit_adam(const bbo_gp_hyper* h, int64_t n, int64_t batch, int32_t ard, int32_t has_scale,
+                    const double* X_dev, const double* y_dev, double* theta_dev, double* adam_m_dev,
+                    double* adam_v_dev, int64_t step0, int64_t epochs, double lr, double sign,
+                    double* values_dev, int32_t* info_dev, void* workspace_dev, size_t workspace_bytes,
+                    void* stream) {
+  if (!hyper_ok(h) || n < 1 || batch < 1 || epochs < 0 || step0 < 0) return BBO_ERR_BAD_SHAPE;
+  if (!X_dev || !y_dev || !theta_dev || !adam_m_dev || !adam_v_dev || !info_dev) return BBO_ERR_BAD_ARG;
+  FitWorkspace w;
+  int rc = w.bind(workspace_dev, workspace_bytes, n, h->d, batch);
+  if (rc != BBO_OK) return rc;
+  return fit_adam(*h, w, ard != 0, has_scale != 0, X_dev, y_dev, theta_dev, adam_m_dev, adam_v_dev, step0,
+                  epochs, lr, sign, values_dev, info_dev, S(stream));
+}
+
+int bbo_gp_theta_to_hyp(int64_t d, int64_t batch, int32_t ard, int32_t has_scale, const double* theta_dev,
+                        double* hyp_dev, void* stream) {
+  if (d < 1 || batch < 1) return BBO_ERR_BAD_SHAPE;
+  if (!theta_dev || !hyp_dev) return BBO_ERR_BAD_ARG;
+  return theta_to_hyp(d, batch, ard != 0, has_scale != 0, theta_dev, hyp_dev, S(stream));
+}
+
+int bbo_gp_factorize(const bbo_gp_hyper* h, int64_t n, int64_t batch, const double* X_dev, const double* y_dev,
+                     const double* hyp_dev, double* linv_dev, double* alpha_dev, double* chol_dev,
+                     double* logdet_dev, int32_t* info_dev, void* workspace_dev, size_t workspace_bytes,
+                     void* stream) {
+  if (!hyper_ok(h) || n < 1 || batch < 1) return BBO_ERR_BAD_SHAPE;
+  if (!X_dev || !y_dev || !hyp_dev || !linv_dev || !alpha_dev || !info_dev) return BBO_ERR_BAD_ARG;
+  FitWorkspace w;
+  int rc = w.bind(workspace_dev, workspace_bytes, n, h->d, batch);
+  if (rc != BBO_OK) return rc;
+  cudaStream_t st = S(stream);
+  const size_t hb = size_t(batch) * (2 * h->d + 2) * sizeof(double);
+  BBO_CUDA_CHECK(cudaMemcpyAsync(w.hyp, hyp_dev, hb, cudaMemcpyDeviceToDevice, st));
+  rc = fit_factor(*h, w, X_dev, y_dev, w.hyp, info_dev, st);
+  if (rc != BBO_OK) return rc;
+  const size_t mb = size_t(batch) * w.np * w.np * sizeof(double);
+  BBO_CUDA_CHECK(cudaMemcpyAsync(linv_dev, w.Wlo, mb, cudaMemcpyDeviceToDevice, st));
+  BBO_CUDA_CHECK(cudaMemcpyAsync(alpha_dev, w.alpha, size_t(batch) * w.np * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, st));
+  if (chol_dev) BBO_CUDA_CHECK(cudaMemcpyAsync(chol_dev, w.L, mb, cudaMemcpyDeviceToDevice, st));
+  if (logdet_dev)
+    BBO_CUDA_CHECK(cudaMemcpyAsync(logdet_dev, w.logdet, size_t(batch) * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  return BBO_OK;
+}
+
+int bbo_gp_make_tf32(int64_t n, const double* linv_dev, float* linv_tf32_dev, void* stream) {
+  if (n < 1) return BBO_ERR_BAD_SHAPE;
+  if (!linv_dev || !linv_tf32_dev) return BBO_ERR_BAD_ARG;
+  return make_tf32(n, linv_dev, linv_tf32_dev, S(stream));
+}
+
+static bool state_ok(const bbo_gp_state* st) {
+  return st && hyper_ok(&st->h) && st->n >= 1 && st->X && st->hyp && st->linv && st->alpha;
+}
+
+int bbo_gp_predict(const bbo_gp_state* st, const double* Xq_dev, int64_t q, double* mu_dev, double* var_dev,
+                   double* cov_full_dev, void* workspace_dev, size_t workspace_bytes, int64_t q_chunk,
+                   void* stream) {
+  if (!state_ok(st) || (q > 0 && !Xq_dev) || q_chunk < 1) return BBO_ERR_BAD_ARG;
+  return gp_predict(*st, Xq_dev, q, mu_dev, var_dev, cov_full_dev, workspace_dev, workspace_bytes, q_chunk,
+                    S(stream));
+}
+
+int bbo_acq_eval(const bbo_acq* a, const void* mu_dev, const void* sigma_dev, void* out_dev, int64_t count,
+                 int32_t is_f32, void* stream) {
+  if (!a || a->kind < BBO_ACQ_EI || a->kind > BBO_ACQ_PI || count < 0) return BBO_ERR_BAD_ARG;
+  if (count > 0 && (!mu_dev || !sigma_dev || !out_dev)) return BBO_ERR_BAD_ARG;
+  return acq_eval(*a, mu_dev, sigma_dev, out_dev, count, is_f32, S(stream));
+}
+
+int bbo_gp_score_pool(const bbo_gp_state* st, const bbo_acq* acq, int32_t precision, const void* Xq_dev,
+                      int32_t xq_is_f32, int64_t q, int64_t index_offset, int32_t k, double* topk_score_dev,
+                      int64_t* topk_index_dev, double* mu_dev, double* var_dev, double* score_dev,
+                      int32_t* nan_count_dev, void* workspace_dev, size_t workspace_bytes, int64_t q_chunk,
+                      int32_t accumulate, void* stream) {
+  if (!state_ok(st) || !acq || acq->kind < BBO_ACQ_EI || acq->kind > BBO_ACQ_PI) return BBO_ERR_BAD_ARG;
+  if ((q > 0 && !Xq_dev) || !topk_score_dev || !topk_index_dev || q_chunk < 1) return BBO_ERR_BAD_ARG;
+  return gp_score_pool(*st, *acq, precision, Xq_dev, xq_is_f32, q, index_offset, k, topk_score_dev,
+                       topk_index_dev, mu_dev, var_dev, score_dev, nan_count_dev, workspace_dev, workspace_bytes,
+                       q_chunk, accumulate != 0, S(stream));
+}
+
+int bbo_gp_score_pool_host(const bbo_gp_state* st, const bbo_acq* acq, int32_t precision, const void* Xq_host,
+                           int32_t xq_is_f32, int64_t q, int64_t index_offset, int32_t k,
+                           double* topk_score_host, int64_t* topk_index_host, void* staging_dev,
+                           double* topk_score_dev, int64_t* topk_index_dev, void* workspace_dev,
+                           size_t workspace_bytes, int64_t q_chunk, void* stream) {
+  if (!state_ok(st) || !acq || acq->kind < BBO_ACQ_EI || acq->kind > BBO_ACQ_PI) return BBO_ERR_BAD_ARG;
+  if ((q > 0 && !Xq_host) || !topk_score_host || !topk_index_host || !staging_dev || !topk_score_dev ||
+      !topk_index_dev || q_chunk < 1 || q < 0)
+    return BBO_ERR_BAD_ARG;
+  cudaStream_t cs = S(stream), copy = nullptr;
+  cudaEvent_t ready[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
+  const int64_t qp = (q_chunk < 128 ? 128 : (q_chunk + 127) / 128 * 128);
+  const size_t esz = xq_is_f32 ? sizeof(float) : sizeof(double);
+  const size_t row = size_t(st->h.d) * esz;
+  int rc = BBO_OK;
+  auto cleanup = [&]() {
+    for (int i = 0; i < 2; ++i) {
+      if (ready[i]) cudaEventDestroy(ready[i]);
+      if (freed[i]) cudaEventDestroy(freed[i]);
+    }
+    if (copy) cudaStreamDestroy(copy);
+  };
+#define BBO_HOST_CHECK(expr)                          \
+  do {                                                \
+    cudaError_t _e = (expr);                          \
+    if (_e != cudaSuccess) {                          \
+      rc = cuda_fail(_e, #expr);                      \
+      cleanup();                                      \
+      return rc;                                      \
+    }                                                 \
+  } while (0)
+  BBO_HOST_CHECK(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    BBO_HOST_CHECK(cudaEventCreateWithFlags(&ready[i], cudaEventDisableTiming));
+    BBO_HOST_CHECK(cudaEventCreateWithFlags(&freed[i], cudaEventDisableTiming));
+  }
+  if (q == 0) {
+    rc = gp_score_pool(*st, *acq, precision, staging_dev, xq_is_f32, 0, index_offset, k, topk_score_dev,
+                       topk_index_dev, nullptr, nullptr, nullptr, nullptr, workspace_dev, workspace_bytes, q_chunk,
+                       false, cs);
+    if (rc != BBO_OK) { cleanup(); return rc; }
+  }
+  int64_t ci = 0;
+  for (int64_t c0 = 0; c0 < q; c0 += qp, ++ci) {
+    const int buf = int(ci & 1);
+    const int64_t qc = (q - c0 < qp) ? q - c0 : qp;
+    char* dst = static_cast<char*>(staging_dev) + size_t(buf) * size_t(qp) * row;
+    if (ci >= 2) BBO_HOST_CHECK(cudaStreamWaitEvent(copy, freed[buf], 0));
+    BBO_HOST_CHECK(cudaMemcpyAsync(dst, static_cast<const char*>(Xq_host) + size_t(c0) * row, size_t(qc) * row,
+                                   cudaMemcpyHostToDevice, copy));
+    BBO_HOST_CHECK(cudaEventRecord(ready[buf], copy));
+    BBO_HOST_CHECK(cudaStreamWaitEvent(cs, ready[buf], 0));
+    rc = gp_score_pool(*st, *acq, precision, dst, xq_is_f32, qc, index_offset + c0, k, topk_score_dev,
+                       topk_index_dev, nullptr, nullptr, nullptr, nullptr, workspace_dev, workspace_bytes, q_chunk,
+                       ci > 0, cs);
+    if (rc != BBO_OK) { cudaStreamSynchronize(copy); cleanup(); return rc; }
+    BBO_HOST_CHECK(cudaEventRecord(freed[buf], cs));
+  }
+  BBO_HOST_CHECK(cudaMemcpyAsync(topk_score_host, topk_score_dev, size_t(k) * sizeof(double),
+                                 cudaMemcpyDeviceToHost, cs));
+  BBO_HOST_CHECK(cudaMemcpyAsync(topk_index_host, topk_index_dev, size_t(k) * sizeof(int64_t),
+                                 cudaMemcpyDeviceToHost, cs));
+  BBO_HOST_CHECK(cudaStreamSynchronize(cs));
+  BBO_HOST_CHECK(cudaStreamSynchronize(copy));
+#undef BBO_HOST_CHECK
+  cleanup();
+  return BBO_OK;
+}
+
+int bbo_topk_merge(const double* score_dev, const int64_t* index_dev, int64_t m, int32_t k,
+                   double* out_score_dev, int64_t* out_index_dev, void* stream) {
+  if (!score_dev || !index_dev || !out_score_dev || !out_index_dev) return BBO_ERR_BAD_ARG;
+  return topk_merge(score_dev, index_dev, m, k, out_score_dev, out_index_dev, S(stream));
+}
+
+int bbo_pool_uniform(uint64_t seed, int64_t row_offset, int64_t q, int64_t d, void* out_dev, int32_t is_f32,
+                     void* stream) {
+  if (q < 0 || d < 1 || (q > 0 && !out_dev)) return BBO_ERR_BAD_ARG;
+  return pool_uniform(seed, row_offset, q, d, out_dev, is_f32, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,532 @@
+// GP posterior + acquisition scoring + top-k selection over a candidate pool.
+//
+// Replaces the body of BODesigner.score_fn (bbo/algorithms/designers/bo/bo.py:110-115):
+//   GP.predict                bbo/algorithms/surrogates/gp/gp.py:75-83
+//   EI / UCB                  bbo/algorithms/designers/bo/acquisitions.py:18-31
+//   get_best_trials           bbo/shared/trial.py:278-294
+//
+// Per chunk of qc candidates (FP64 mode):
+//   k_kstar     Ks[c,j] = s2 k(x_c, X_j)  (exact-difference form), mu_c = const + Ks[c,:] alpha
+//   k_vnorm     |L^-1 k*_c|^2 = sum_i (sum_{j<=i} Ks[c,j] Linv[i,j])^2 : DMMA panel GEMM whose
+//               epilogue squares and row-sums the accumulators, so V is never written
+//   k_acq       var = k(x,x) - |v|^2 + noise, sd = sqrt(var), EI/UCB/PI
+//   k_topk_seg  per-segment top-k (descending score, ties -> lowest index), applied in levels
+// The TF32 mode swaps k_kstar/k_vnorm for the tcgen05 pipeline in score_tf32.cu.
+#include "score.cuh"
+
+#include "fit.cuh"
+#include "gemm_f64.cuh"
+
+namespace bbo {
+
+constexpr int kDC = 32;
+constexpr int kXS = kDC + 1;
+constexpr int kSeg = 2048;  // top-k segment length
+
+// same tile routine as fit.cu (kept local so each TU is self-contained)
+template <typename T1>
+__device__ __forceinline__ void dist_tile_q(const T1* __restrict__ X1, int64_t n1, int64_t i0,
+                                            const double* __restrict__ X2, int64_t n2, int64_t j0, int d,
+                                            const double* __restrict__ invl, double eps, double (&s)[4][4],
+                                            double* x1s, double* x2s, double* ils) {
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) s[a][b] = 0.0;
+  for (int kc = 0; kc < d; kc += kDC) {
+    const int kw = min(kDC, d - kc);
+    __syncthreads();
+    for (int idx = tid; idx < 64 * kDC; idx += 256) {
+      int r = idx / kDC, k = idx % kDC;
+      double v1 = 0.0, v2 = 0.0;
+      if (k < kw) {
+        if (i0 + r < n1) v1 = static_cast<double>(X1[(i0 + r) * d + kc + k]);
+        if (j0 + r < n2) v2 = X2[(j0 + r) * d + kc + k];
+      }
+      x1s[r * kXS + k] = v1;
+      x2s[r * kXS + k] = v2;
+    }
+    if (tid < kDC) ils[tid] = tid < kw ? invl[kc + tid] : 0.0;
+    __syncthreads();
+    for (int k = 0; k < kw; ++k) {
+      const double il = ils[k];
+      double av[4], bv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) av[a] = x1s[(ty * 4 + a) * kXS + k];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) bv[b] = x2s[(tx + 16 * b) * kXS + k];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          double de = (bv[b] - av[a]) * il + eps;
+          s[a][b] = fma(de, de, s[a][b]);
+        }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Ks (qc_pad, np) and mu.  grid (qc_pad/64), 256 threads.
+// ------------------------------------------------------------------------------------------
+template <typename T1>
+__global__ void __launch_bounds__(256)
+k_kstar(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const double* __restrict__ X, int64_t n,
+        int64_t np, const double* __restrict__ hyp, const double* __restrict__ alpha,
+        double* __restrict__ Ks, double* __restrict__ mu) {
+  __shared__ double x1s[64 * kXS], x2s[64 * kXS], ils[kDC];
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int64_t c0 = int64_t(blockIdx.x) * 64;
+  const double eps = h.kind == BBO_KERNEL_MATERN52 ? h.pairwise_eps : 0.0;
+  const double s2 = hyp[2 * h.d];
+  double macc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int64_t j0 = 0; j0 < np; j0 += 64) {
+    double s[4][4];
+    dist_tile_q<T1>(Xq, qc, c0, X, n, j0, h.d, hyp + h.d, eps, s, x1s, x2s, ils);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int64_t j = j0 + tx + 16 * b;
+        double v = (j < n) ? s2 * kernel_from_s(h.kind, s[a][b]) : 0.0;
+        Ks[(c0 + ty * 4 + a) * np + j] = v;
+        macc[a] = fma(v, alpha[j], macc[a]);
+      }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    double v = macc[a];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (tx == 0) mu[c0 + ty * 4 + a] = hyp[2 * h.d + 1] + v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// vpart[split, c] = sum over this split's row tiles i of (sum_{j<=i} Ks[c,j] Linv[i,j])^2
+// grid (qc_pad/128, nsplit), Cfg128x64.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(Cfg128x64::THREADS)
+k_vnorm(const double* __restrict__ Ks, const double* __restrict__ Linv, int64_t np, int64_t qc_pad,
+        double* __restrict__ vpart) {
+  using Cfg = Cfg128x64;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ double red[Cfg::BM][Cfg::WARPS_N];
+  const int64_t c0 = int64_t(blockIdx.x) * Cfg::BM;
+  const double* A = Ks + c0 * np;
+  double rs[Cfg::MF];
+#pragma unroll
+  for (int i = 0; i < Cfg::MF; ++i) rs[i] = 0.0;
+  const int ntile = int(np / 64);
+  for (int it = blockIdx.y; it < ntile; it += gridDim.y) {
+    Acc<Cfg> acc;
+    acc.zero();
+    gemm_nt_mainloop<Cfg>(A, np, Linv + int64_t(it) * 64 * np, np, 0, (it + 1) * 64, acc, smem);
+#pragma unroll
+    for (int i = 0; i < Cfg::MF; ++i)
+#pragma unroll
+      for (int j = 0; j < Cfg::NF; ++j) {
+        rs[i] = fma(acc.v[i][j][0], acc.v[i][j][0], rs[i]);
+        rs[i] = fma(acc.v[i][j][1], acc.v[i][j][1], rs[i]);
+      }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = warp / Cfg::WARPS_N, wn = warp % Cfg::WARPS_N;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int i = 0; i < Cfg::MF; ++i) {
+    double v = rs[i];
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (t == 0) red[wm * Cfg::WM + i * 8 + g][wn] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < Cfg::BM) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < Cfg::WARPS_N; ++w) v += red[threadIdx.x][w];
+    vpart[int64_t(blockIdx.y) * qc_pad + c0 + threadIdx.x] = v;
+  }
+}
+
+// V[c,i] = sum_{j<=i} Ks[c,j] Linv[i,j]  (only for the full-covariance predict).
+// grid (qc_pad/64, np/64), Cfg64x64.
+__global__ void __launch_bounds__(Cfg64x64::THREADS)
+k_vstore(const double* __restrict__ Ks, const double* __restrict__ Linv, int64_t np, double* __restrict__ V) {
+  using Cfg = Cfg64x64;
+  extern __shared__ __align__(16) double smem[];
+  const int64_t c0 = int64_t(blockIdx.x) * 64, i0 = int64_t(blockIdx.y) * 64;
+  Acc<Cfg> acc;
+  acc.zero();
+  gemm_nt_mainloop<Cfg>(Ks + c0 * np, np, Linv + i0 * np, np, 0, int(i0) + 64, acc, smem);
+  double* C = V + c0 * np + i0;
+  acc_foreach<Cfg>(acc, [&](int r, int c, double v0, double v1) {
+    *reinterpret_cast<double2*>(C + int64_t(r) * np + c) = make_double2(v0, v1);
+  });
+}
+
+// C[i,j] -= sum_k V[i,k] V[j,k] for i,j < q (C is (q,q), ld = q).  grid (qp/64, qp/64), Cfg64x64.
+__global__ void __launch_bounds__(Cfg64x64::THREADS)
+k_cov_sub(const double* __restrict__ V, int64_t np, double* __restrict__ C, int64_t q) {
+  using Cfg = Cfg64x64;
+  extern __shared__ __align__(16) double smem[];
+  const int64_t i0 = int64_t(blockIdx.x) * 64, j0 = int64_t(blockIdx.y) * 64;
+  Acc<Cfg> acc;
+  acc.zero();
+  gemm_nt_mainloop<Cfg>(V + i0 * np, np, V + j0 * np, np, 0, int(np), acc, smem);
+  acc_foreach<Cfg>(acc, [&](int r, int c, double v0, double v1) {
+    int64_t i = i0 + r, j = j0 + c;
+    if (i < q) {
+      if (j < q) C[i * q + j] -= v0;
+      if (j + 1 < q) C[i * q + j + 1] -= v1;
+    }
+  });
+}
+
+// ------------------------------------------------------------------------------------------
+// acquisition (acquisitions.py:18-31) from mu and sum of |v|^2 partials.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T acq_value(const bbo_acq& a, T mu, T sd) {
+  if (a.kind == BBO_ACQ_UCB) return mu + T(a.beta) * sd;
+  const T imp = mu - T(a.best_f) - T(a.eps);
+  const T z = imp / sd;
+  const T Phi = T(0.5) * (T(1) + erf(z * T(0.70710678118654752440)));  // Normal(0,1).cdf
+  if (a.kind == BBO_ACQ_PI) return Phi;
+  const T phi = exp(T(-0.5) * z * z - T(0.91893853320467274178));      // exp(log_prob)
+  return imp * Phi + sd * phi;
+}
+
+__global__ void __launch_bounds__(256)
+k_acq(bbo_gp_hyper h, bbo_acq a, int has_acq, int clamp_var, const double* __restrict__ hyp,
+      const double* __restrict__ mu, const double* __restrict__ vpart, int nsplit, int64_t qc_pad, int64_t qc,
+      double* __restrict__ score_ws, double* __restrict__ mu_out, double* __restrict__ var_out,
+      double* __restrict__ score_out, int32_t* __restrict__ nan_count) {
+  const int64_t c = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (c >= qc) return;
+  const double eps = h.kind == BBO_KERNEL_MATERN52 ? h.pairwise_eps : 0.0;
+  const double kxx = hyp[2 * h.d] * kernel_from_s(h.kind, double(h.d) * eps * eps);
+  double vn = 0.0;
+  for (int s = 0; s < nsplit; ++s) vn += vpart[int64_t(s) * qc_pad + c];
+  double var = kxx - vn + h.noise;
+  if (clamp_var) var = fmax(var, 0.0);
+  const double m = mu[c];
+  if (mu_out) mu_out[c] = m;
+  if (var_out) var_out[c] = var;
+  if (has_acq) {
+    const double sc = acq_value<double>(a, m, sqrt(var));
+    score_ws[c] = sc;
+    if (score_out) score_out[c] = sc;
+    if (sc != sc && nan_count) atomicAdd(nan_count, 1);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_acq_elem(bbo_acq a, const T* __restrict__ mu, const T* __restrict__ sd, T* __restrict__ out, int64_t n) {
+  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (i < n) out[i] = acq_value<T>(a, mu[i], sd[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Segment top-k: block b scans entries [b*kSeg, (b+1)*kSeg) of (score, index) and emits its k
+// best in order.  idx_in == nullptr -> index = base + position.  NaN scores and index < 0 are
+// skipped; missing slots are (-inf, -1).  256 threads.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_topk_seg(const double* __restrict__ score, const int64_t* __restrict__ idx_in, int64_t base, int64_t m,
+           int k, double* __restrict__ out_s, int64_t* __restrict__ out_i) {
+  __shared__ double ss[kSeg];
+  __shared__ int64_t si[kSeg];
+  __shared__ double ws[8];
+  __shared__ int64_t wi[8];
+  __shared__ int wp[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t s0 = int64_t(blockIdx.x) * kSeg;
+  for (int p = tid; p < kSeg; p += 256) {
+    const int64_t g = s0 + p;
+    double sc = -INFINITY;
+    int64_t ix = -1;
+    if (g < m) {
+      sc = score[g];
+      ix = idx_in ? idx_in[g] : base + g;
+      if (sc != sc) ix = -1;
+    }
+    ss[p] = sc;
+    si[p] = ix;
+  }
+  __syncthreads();
+  for (int r = 0; r < k; ++r) {
+    double bs = -INFINITY;
+    int64_t bi = -1;
+    int bp = -1;
+#pragma unroll
+    for (int u = 0; u < kSeg / 256; ++u) {
+      const int p = tid + u * 256;
+      if (better(ss[p], si[p], bs, bi)) {
+        bs = ss[p];
+        bi = si[p];
+        bp = p;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      double os = __shfl_xor_sync(0xffffffffu, bs, o);
+      int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      int op = __shfl_xor_sync(0xffffffffu, bp, o);
+      if (better(os, oi, bs, bi)) {
+        bs = os;
+        bi = oi;
+        bp = op;
+      }
+    }
+    if (lane == 0) {
+      ws[warp] = bs;
+      wi[warp] = bi;
+      wp[warp] = bp;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double fs = ws[0];
+      int64_t fi = wi[0];
+      int fp = wp[0];
+      for (int w = 1; w < 8; ++w)
+        if (better(ws[w], wi[w], fs, fi)) {
+          fs = ws[w];
+          fi = wi[w];
+          fp = wp[w];
+        }
+      out_s[int64_t(blockIdx.x) * k + r] = fi >= 0 ? fs : -INFINITY;
+      out_i[int64_t(blockIdx.x) * k + r] = fi;
+      if (fp >= 0) si[fp] = -1;  // taken
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void k_topk_init(double* s, int64_t* i, int k) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < k) {
+    s[t] = -INFINITY;
+    i[t] = -1;
+  }
+}
+
+// reduce m (score,index) pairs in buf A to k pairs in (out_s,out_i), ping-ponging through buf B
+static int topk_levels(double* as, int64_t* ai, int64_t m, double* bs, int64_t* bi, int k, double* out_s,
+                       int64_t* out_i, cudaStream_t st) {
+  while (true) {
+    const int64_t nb = ceil_div(m, kSeg);
+    if (nb == 1) {
+      k_topk_seg<<<1, 256, 0, st>>>(as, ai, 0, m, k, out_s, out_i);
+      BBO_LAUNCH_CHECK();
+      return BBO_OK;
+    }
+    k_topk_seg<<<unsigned(nb), 256, 0, st>>>(as, ai, 0, m, k, bs, bi);
+    BBO_LAUNCH_CHECK();
+    double* ts = as;
+    as = bs;
+    bs = ts;
+    int64_t* ti = ai;
+    ai = bi;
+    bi = ti;
+    m = nb * k;
+  }
+}
+
+int topk_merge(const double* score, const int64_t* index, int64_t m, int k, double* out_s, int64_t* out_i,
+               cudaStream_t st) {
+  if (k < 1 || k > BBO_TOPK_MAX || m < 0) return BBO_ERR_BAD_ARG;
+  if (m > kSeg) return BBO_ERR_BAD_SHAPE;  // gathered lists are tiny: G * k <= 8 * 128
+  k_topk_seg<<<1, 256, 0, st>>>(score, index, 0, m, k, out_s, out_i);
+  BBO_LAUNCH_CHECK();
+  return BBO_OK;
+}
+
+// ==========================================================================================
+// workspace + drivers
+// ==========================================================================================
+static int64_t round_chunk(int64_t q_chunk) { return ceil_div(q_chunk < 128 ? 128 : q_chunk, 128) * 128; }
+
+static int pick_nsplit(int64_t qc_pad, int64_t np) {
+  int64_t want = ceil_div(2 * 148, qc_pad / 128);
+  int64_t cap = np / 64;
+  if (want > cap) want = cap;
+  if (want > kMaxSplit) want = kMaxSplit;
+  if (want < 1) want = 1;
+  return int(want);
+}
+
+size_t ScoreWorkspace::bytes(int64_t n, int64_t d, int64_t q_chunk, int precision, bool want_full) {
+  const int64_t np = padded(n), qp = round_chunk(q_chunk);
+  const int64_t nblk = ceil_div(qp, kSeg);
+  size_t doubles = size_t(qp) * np * (want_full ? 2 : 1)  // Ks (+V)
+                   + size_t(kMaxSplit) * qp + 2 * size_t(qp)  // vpart, mu, score
+                   + 2 * size_t(BBO_TOPK_MAX) * (nblk + 1) * 2;  // two (score,index) ping-pong lists
+  size_t extra = 0;
+  if (precision == BBO_PREC_TF32) extra = score_tf32_extra_bytes(n, d, qp);
+  return doubles * sizeof(double) + extra + 512;
+}
+
+int ScoreWorkspace::bind(void* ws, size_t ws_bytes, int64_t n, int64_t d, int64_t q_chunk, int precision,
+                         bool want_full) {
+  np = padded(n);
+  qp = round_chunk(q_chunk);
+  if (ws == nullptr || ws_bytes < bytes(n, d, q_chunk, precision, want_full)) return BBO_ERR_WORKSPACE;
+  uintptr_t p = (reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255);
+  double* q = reinterpret_cast<double*>(p);
+  Ks = q;
+  q += size_t(qp) * np;
+  V = want_full ? q : nullptr;
+  if (want_full) q += size_t(qp) * np;
+  vpart = q;
+  q += size_t(kMaxSplit) * qp;
+  mu = q;
+  q += qp;
+  score = q;
+  q += qp;
+  const int64_t nblk = ceil_div(qp, kSeg);
+  list_len = int64_t(BBO_TOPK_MAX) * (nblk + 1);
+  la_s = q;
+  q += list_len;
+  lb_s = q;
+  q += list_len;
+  la_i = reinterpret_cast<int64_t*>(q);
+  q += list_len;
+  lb_i = reinterpret_cast<int64_t*>(q);
+  q += list_len;
+  tf32 = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(q) + 255) & ~uintptr_t(255));
+  return BBO_OK;
+}
+
+static bool g_attr_done = false;
+static int set_smem_attrs() {
+  if (g_attr_done) return BBO_OK;
+  BBO_CUDA_CHECK(cudaFuncSetAttribute(k_vnorm, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      int(Cfg128x64::SMEM_BYTES)));
+  BBO_CUDA_CHECK(cudaFuncSetAttribute(k_vstore, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      int(Cfg64x64::SMEM_BYTES)));
+  BBO_CUDA_CHECK(cudaFuncSetAttribute(k_cov_sub, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      int(Cfg64x64::SMEM_BYTES)));
+  g_attr_done = true;
+  return BBO_OK;
+}
+
+// mu and |v|^2 partials for one chunk (FP64 or TF32)
+static int posterior_chunk(const bbo_gp_state& s, const ScoreWorkspace& w, int precision, const void* Xq,
+                           int xq_is_f32, int64_t qc, int* nsplit_out, cudaStream_t st) {
+  const int64_t qc_pad = ceil_div(qc, 128) * 128;
+  if (precision == BBO_PREC_TF32) {
+    *nsplit_out = 1;
+    return score_tf32_chunk(s, w, Xq, xq_is_f32, qc, qc_pad, st);
+  }
+  const int nsplit = pick_nsplit(qc_pad, w.np);
+  *nsplit_out = nsplit;
+  if (xq_is_f32)
+    k_kstar<float><<<unsigned(qc_pad / 64), 256, 0, st>>>(s.h, static_cast<const float*>(Xq), qc, s.X, s.n, w.np,
+                                                         s.hyp, s.alpha, w.Ks, w.mu);
+  else
+    k_kstar<double><<<unsigned(qc_pad / 64), 256, 0, st>>>(s.h, static_cast<const double*>(Xq), qc, s.X, s.n,
+                                                          w.np, s.hyp, s.alpha, w.Ks, w.mu);
+  BBO_LAUNCH_CHECK();
+  k_vnorm<<<dim3(unsigned(qc_pad / 128), unsigned(nsplit)), Cfg128x64::THREADS, Cfg128x64::SMEM_BYTES, st>>>(
+      w.Ks, s.linv, w.np, w.qp, w.vpart);
+  BBO_LAUNCH_CHECK();
+  return BBO_OK;
+}
+
+int gp_predict(const bbo_gp_state& s, const double* Xq, int64_t q, double* mu, double* var, double* cov_full,
+               void* ws, size_t ws_bytes, int64_t q_chunk, cudaStream_t st) {
+  if (q < 0 || s.n < 1 || s.h.d < 1) return BBO_ERR_BAD_SHAPE;
+  if (q == 0) return BBO_OK;
+  int rc = set_smem_attrs();
+  if (rc != BBO_OK) return rc;
+  const bool full = cov_full != nullptr;
+  ScoreWorkspace w;
+  rc = w.bind(ws, ws_bytes, s.n, s.h.d, q_chunk, BBO_PREC_FP64, full);
+  if (rc != BBO_OK) return rc;
+  if (full && q > w.qp) return BBO_ERR_BAD_SHAPE;
+  bbo_acq none{};
+  for (int64_t c0 = 0; c0 < q; c0 += w.qp) {
+    const int64_t qc = (q - c0 < w.qp) ? q - c0 : w.qp;
+    int nsplit = 1;
+    rc = posterior_chunk(s, w, BBO_PREC_FP64, Xq + c0 * s.h.d, 0, qc, &nsplit, st);
+    if (rc != BBO_OK) return rc;
+    k_acq<<<unsigned(ceil_div(qc, 256)), 256, 0, st>>>(s.h, none, 0, 0, s.hyp, w.mu, w.vpart, nsplit, w.qp, qc,
+                                                       w.score, mu ? mu + c0 : nullptr, var ? var + c0 : nullptr,
+                                                       nullptr, nullptr);
+    BBO_LAUNCH_CHECK();
+    if (full) {
+      // gp.py:81-82: cov(Xq,Xq) - v^T v + noise I
+      const int64_t qc_pad = ceil_div(qc, 128) * 128;
+      k_vstore<<<dim3(unsigned(qc_pad / 64), unsigned(w.np / 64)), Cfg64x64::THREADS, Cfg64x64::SMEM_BYTES, st>>>(
+          w.Ks, s.linv, w.np, w.V);
+      BBO_LAUNCH_CHECK();
+      rc = cov_matrix(s.h, s.hyp, Xq, q, Xq, q, cov_full, q, s.h.noise, st);
+      if (rc != BBO_OK) return rc;
+      k_cov_sub<<<dim3(unsigned(ceil_div(q, 64)), unsigned(ceil_div(q, 64))), Cfg64x64::THREADS,
+                  Cfg64x64::SMEM_BYTES, st>>>(w.V, w.np, cov_full, q);
+      BBO_LAUNCH_CHECK();
+    }
+  }
+  return BBO_OK;
+}
+
+int gp_score_pool(const bbo_gp_state& s, const bbo_acq& acq, int precision, const void* Xq, int xq_is_f32,
+                  int64_t q, int64_t index_offset, int k, double* topk_s, int64_t* topk_i, double* mu_out,
+                  double* var_out, double* score_out, int32_t* nan_count, void* ws, size_t ws_bytes,
+                  int64_t q_chunk, bool keep_running, cudaStream_t st) {
+  if (q < 0 || s.n < 1 || s.h.d < 1) return BBO_ERR_BAD_SHAPE;
+  if (k < 1 || k > BBO_TOPK_MAX) return BBO_ERR_BAD_ARG;
+  if (precision != BBO_PREC_FP64 && precision != BBO_PREC_TF32) return BBO_ERR_BAD_ARG;
+  if (precision == BBO_PREC_TF32 && s.linv_tf32 == nullptr) return BBO_ERR_BAD_ARG;
+  int rc = set_smem_attrs();
+  if (rc != BBO_OK) return rc;
+  ScoreWorkspace w;
+  rc = w.bind(ws, ws_bytes, s.n, s.h.d, q_chunk, precision, false);
+  if (rc != BBO_OK) return rc;
+  if (!keep_running) {
+    k_topk_init<<<1, BBO_TOPK_MAX, 0, st>>>(topk_s, topk_i, k);
+    BBO_LAUNCH_CHECK();
+  }
+  const size_t esz = xq_is_f32 ? sizeof(float) : sizeof(double);
+  for (int64_t c0 = 0; c0 < q; c0 += w.qp) {
+    const int64_t qc = (q - c0 < w.qp) ? q - c0 : w.qp;
+    const void* xq = static_cast<const char*>(Xq) + size_t(c0) * s.h.d * esz;
+    int nsplit = 1;
+    rc = posterior_chunk(s, w, precision, xq, xq_is_f32, qc, &nsplit, st);
+    if (rc != BBO_OK) return rc;
+    k_acq<<<unsigned(ceil_div(qc, 256)), 256, 0, st>>>(
+        s.h, acq, 1, precision == BBO_PREC_TF32, s.hyp, w.mu, w.vpart, nsplit, w.qp, qc, w.score,
+        mu_out ? mu_out + c0 : nullptr, var_out ? var_out + c0 : nullptr, score_out ? score_out + c0 : nullptr,
+        nan_count);
+    BBO_LAUNCH_CHECK();
+    // level 1: segments of this chunk -> list A (after the k running entries)
+    const int64_t nb = ceil_div(qc, kSeg);
+    BBO_CUDA_CHECK(cudaMemcpyAsync(w.la_s, topk_s, size_t(k) * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    BBO_CUDA_CHECK(cudaMemcpyAsync(w.la_i, topk_i, size_t(k) * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    k_topk_seg<<<unsigned(nb), 256, 0, st>>>(w.score, nullptr, index_offset + c0, qc, k, w.la_s + k, w.la_i + k);
+    BBO_LAUNCH_CHECK();
+    rc = topk_levels(w.la_s, w.la_i, (nb + 1) * k, w.lb_s, w.lb_i, k, topk_s, topk_i, st);
+    if (rc != BBO_OK) return rc;
+  }
+  return BBO_OK;
+}
+
+int acq_eval(const bbo_acq& a, const void* mu, const void* sd, void* out, int64_t n, int is_f32,
+             cudaStream_t st) {
+  if (n <= 0) return BBO_OK;
+  if (is_f32)
+    k_acq_elem<float><<<unsigned(ceil_div(n, 256)), 256, 0, st>>>(a, static_cast<const float*>(mu),
+                                                                 static_cast<const float*>(sd),
+                                                                 static_cast<float*>(out), n);
+  else
+    k_acq_elem<double><<<unsigned(ceil_div(n, 256)), 256, 0, st>>>(a, static_cast<const double*>(mu),
+                                                                  static_cast<const double*>(sd),
+                                                                  static_cast<double*>(out), n);
+  BBO_LAUNCH_CHECK();
+  return BBO_OK;
+}
+
+}  // namespace bbo

@@ -1,0 +1,43 @@
+// Host-side declarations of the scoring path (score.cu, score_tf32.cu).
+#pragma once
+#include "common.cuh"
+
+namespace bbo {
+
+constexpr int kMaxSplit = 32;  // max row-tile splits of the variance panel per candidate tile
+
+struct ScoreWorkspace {
+  int64_t np = 0, qp = 0;      // padded n, padded chunk length
+  double* Ks = nullptr;        // (qp, np)  cross-covariance of the current chunk
+  double* V = nullptr;         // (qp, np)  L^-1 k*, only for the full-covariance predict
+  double* vpart = nullptr;     // (kMaxSplit, qp) partial |v|^2
+  double* mu = nullptr;        // (qp)
+  double* score = nullptr;     // (qp)
+  int64_t list_len = 0;
+  double *la_s = nullptr, *lb_s = nullptr;   // top-k ping-pong lists
+  int64_t *la_i = nullptr, *lb_i = nullptr;
+  void* tf32 = nullptr;        // TF32-mode scratch (score_tf32.cu)
+
+  static size_t bytes(int64_t n, int64_t d, int64_t q_chunk, int precision, bool want_full);
+  int bind(void* ws, size_t ws_bytes, int64_t n, int64_t d, int64_t q_chunk, int precision, bool want_full);
+};
+
+int gp_predict(const bbo_gp_state& s, const double* Xq, int64_t q, double* mu, double* var, double* cov_full,
+               void* ws, size_t ws_bytes, int64_t q_chunk, cudaStream_t st);
+int gp_score_pool(const bbo_gp_state& s, const bbo_acq& acq, int precision, const void* Xq, int xq_is_f32,
+                  int64_t q, int64_t index_offset, int k, double* topk_s, int64_t* topk_i, double* mu_out,
+                  double* var_out, double* score_out, int32_t* nan_count, void* ws, size_t ws_bytes,
+                  int64_t q_chunk, bool keep_running, cudaStream_t st);
+int acq_eval(const bbo_acq& a, const void* mu, const void* sd, void* out, int64_t n, int is_f32, cudaStream_t st);
+int topk_merge(const double* score, const int64_t* index, int64_t m, int k, double* out_s, int64_t* out_i,
+               cudaStream_t st);
+
+// TF32 mode (score_tf32.cu): fills w.mu and w.vpart[0, :] for one chunk
+size_t score_tf32_extra_bytes(int64_t n, int64_t d, int64_t qp);
+int score_tf32_chunk(const bbo_gp_state& s, const ScoreWorkspace& w, const void* Xq, int xq_is_f32, int64_t qc,
+                     int64_t qc_pad, cudaStream_t st);
+int make_tf32(int64_t n, const double* linv, float* out, cudaStream_t st);
+
+int pool_uniform(uint64_t seed, int64_t row_offset, int64_t q, int64_t d, void* out, int is_f32, cudaStream_t st);
+
+}  // namespace bbo

@@ -1,0 +1,234 @@
+/*
+ * bbo_b200.h -- C ABI of the B200-native GP-BO hot path (libbbo_b200.so).
+ *
+ * Drop-in boundary for songlei00/bbo's Gaussian-process surrogate + acquisition
+ * scoring.  Every entry point replaces a specific piece of reference Python
+ * (paths relative to the reference repo root):
+ *
+ *   bbo_gp_fit_value_grad   bbo/algorithms/surrogates/gp/objectives.py:34-45 (value)
+ *                           + loss.backward() at gp/gp.py:62 (gradient)
+ *   bbo_gp_fit_adam         bbo/algorithms/surrogates/gp/gp.py:54-63 (GP.train loop)
+ *   bbo_gp_factorize        bbo/algorithms/surrogates/gp/objectives.py:20-31
+ *                           (solve_gp_linear_system, cached at gp/gp.py:66-74)
+ *   bbo_gp_predict          bbo/algorithms/surrogates/gp/gp.py:75-83 (GP.predict)
+ *   bbo_gp_score_pool       gp/gp.py:75-83 + designers/bo/acquisitions.py:18-31
+ *                           + shared/trial.py:278-294 (get_best_trials), i.e. the
+ *                           body of BODesigner.score_fn (designers/bo/bo.py:110-115)
+ *                           and DesignerAsOptimizer.optimize's selection
+ *                           (optimizers/designer_optimizer.py:29-42)
+ *   bbo_gp_score_pool_host  same, candidates in HOST memory (H2D overlapped)
+ *   bbo_cov_matrix          bbo/algorithms/surrogates/gp/kernel_impl.py:40-128
+ *                           (KernelProtocol: rbf/matern52, vmap and cdist forms)
+ *   bbo_acq_eval            bbo/algorithms/designers/bo/acquisitions.py:18-31
+ *   bbo_topk_merge          bbo/shared/trial.py:285-294 over gathered per-GPU lists
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer marked "dev" is CUDA device
+ *     memory owned by the caller (the library never allocates device memory and
+ *     keeps no global state); "host" pointers are host memory.
+ *   - all matrices row-major, contiguous; float64 unless stated.
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it
+ *     unless the description says they synchronise.
+ *   - return value: BBO_OK or a bbo_status; numerical failures (non-PD matrix,
+ *     NaN scores) are reported through device-side `info` words so that nothing
+ *     synchronises implicitly:
+ *         info[b] == 0            ok
+ *         info[b] == j+1  (>0)    leading minor j of K is not positive definite
+ *                                 (what makes torch.linalg.cholesky raise at
+ *                                 objectives.py:29)
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point
+ *     returns BBO_ERR_CUDA.
+ */
+#ifndef BBO_B200_H_
+#define BBO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum bbo_status {
+  BBO_OK = 0,
+  BBO_ERR_BAD_SHAPE = 1,
+  BBO_ERR_BAD_ARG = 2,
+  BBO_ERR_WORKSPACE = 3,   /* workspace too small */
+  BBO_ERR_CUDA = 4,        /* CUDA runtime error (see bbo_last_cuda_error) */
+  BBO_ERR_NOT_PD = 5,      /* only from the synchronising *_host helpers */
+  BBO_ERR_NAN = 6
+} bbo_status;
+
+/* kernel_impl.py:29-34 */
+typedef enum bbo_kernel_kind { BBO_KERNEL_RBF = 0, BBO_KERNEL_MATERN52 = 1 } bbo_kernel_kind;
+/* acquisitions.py:13-31 (+PI, absent from the reference) */
+typedef enum bbo_acq_kind { BBO_ACQ_EI = 0, BBO_ACQ_UCB = 1, BBO_ACQ_PI = 2 } bbo_acq_kind;
+/* arithmetic of the n^2 panel of the scoring pass */
+typedef enum bbo_precision { BBO_PREC_FP64 = 0, BBO_PREC_TF32 = 1 } bbo_precision;
+
+#define BBO_ROW_ALIGN 128   /* n is padded to a multiple of this in all n x n buffers */
+#define BBO_TOPK_MAX 128
+
+int bbo_version(void);
+/* text of the last CUDA error seen by this thread ("" if none) */
+const char* bbo_last_cuda_error(void);
+/* n rounded up to BBO_ROW_ALIGN */
+int64_t bbo_padded_n(int64_t n);
+
+/* ---- hyper-parameters (constrained values, i.e. after softplus, kernels.py:35,52) */
+typedef struct bbo_gp_hyper {
+  int32_t kind;           /* bbo_kernel_kind */
+  int32_t d;              /* feature dimension */
+  double pairwise_eps;    /* 1e-6 for matern52_vmap (torch.nn.PairwiseDistance eps,
+                             kernel_impl.py:60,94), 0 for the cdist forms and RBF */
+  double noise;           /* fixed noise variance (gp.py:41) */
+} bbo_gp_hyper;
+
+/* Device layout of one problem's hyper-parameter block `hyp` (float64[2*d+2]):
+ *   [0,d)      lengthscale l_k (isotropic kernels replicate the scalar)
+ *   [d,2d)     1 / l_k
+ *   [2d]       output variance s^2 (1.0 when there is no ScaleKernel)
+ *   [2d+1]     mean constant c (means.py:22)                                     */
+static inline int64_t bbo_hyp_len(int64_t d) { return 2 * d + 2; }
+
+/* ---- workspace sizing --------------------------------------------------------- */
+/* bytes of device workspace needed by bbo_gp_fit_value_grad / bbo_gp_fit_adam /
+ * bbo_gp_factorize for `batch` problems of n observations in d dims.            */
+size_t bbo_gp_fit_workspace_bytes(int64_t n, int64_t d, int64_t batch);
+/* bytes needed by bbo_gp_predict / bbo_gp_score_pool for chunks of `q_chunk`
+ * candidates (q_chunk is rounded up to 128 internally).                          */
+size_t bbo_gp_score_workspace_bytes(int64_t n, int64_t d, int64_t q_chunk, int32_t precision);
+/* bytes needed by bbo_gp_predict; want_full != 0 when cov_full_dev will be requested.       */
+size_t bbo_gp_predict_workspace_bytes(int64_t n, int64_t d, int64_t q_chunk, int32_t want_full);
+
+/* ---- covariance: KernelProtocol(X1, X2, lengthscale) -> (q, n) ------------------
+ * out[i*ldo + j] = s2 * k(X1_i, X2_j);  X1 (q,d), X2 (n,d) dev; hyp dev (layout above) */
+int bbo_cov_matrix(const bbo_gp_hyper* h, const double* hyp_dev, const double* X1_dev, int64_t q,
+                   const double* X2_dev, int64_t n, double* out_dev, int64_t ldo, void* stream);
+
+/* ---- fit: value and gradient of objectives.py:34-45 ---------------------------------
+ * For b in [0,batch): X (batch,n,d), y (batch,n), hyp (batch, 2d+2).
+ * Outputs (dev): value[b] = -1/2 dY^T K^-1 dY - sum log L_ii - n/2 log 2pi  (this IS
+ * +log p(y); the reference's name is misleading),
+ * grad[b, 0:d] = d value / d l_k, grad[b,d] = d value / d s2, grad[b,d+1] = d value / d c,
+ * info[b] as described above.  Gradients are w.r.t. the constrained values; the raw
+ * (pre-softplus) chain rule is applied by bbo_gp_fit_adam or by the caller.           */
+int bbo_gp_fit_value_grad(const bbo_gp_hyper* h, int64_t n, int64_t batch, const double* X_dev,
+                          const double* y_dev, const double* hyp_dev, double* value_dev,
+                          double* grad_dev, int32_t* info_dev, void* workspace_dev,
+                          size_t workspace_bytes, void* stream);
+
+/* ---- train: GP.train (gp.py:54-63) entirely on the device ----------------------------
+ * theta (batch, P) raw parameters in the reference's Adam order (gp.py:55):
+ *   [0] mean constant, [1 .. 1+n_ls) raw lengthscale (n_ls = d for ARD, 1 isotropic),
+ *   [1+n_ls] raw output variance (present iff has_scale).  P = 1 + n_ls + has_scale.
+ * adam_m, adam_v (batch, P) moment buffers (zero them before the first call);
+ * step0 = number of Adam steps already taken (bias correction continues from it).
+ * Runs `epochs` iterations of: value/grad -> chain rule through softplus -> Adam
+ * (lr, betas 0.9/0.999, eps 1e-8: torch.optim.Adam defaults) minimising
+ * sign * value  (sign=+1 reproduces the reference, which minimises +log p; sign=-1
+ * minimises the true negative log-likelihood).  values_dev (epochs, batch) receives
+ * the value seen at each epoch (may be NULL).  No host synchronisation.
+ * A non-PD epoch sets info[b] and freezes that problem's parameters.                   */
+int bbo_gp_fit_adam(const bbo_gp_hyper* h, int64_t n, int64_t batch, int32_t ard, int32_t has_scale,
+                    const double* X_dev, const double* y_dev, double* theta_dev, double* adam_m_dev,
+                    double* adam_v_dev, int64_t step0, int64_t epochs, double lr, double sign,
+                    double* values_dev, int32_t* info_dev, void* workspace_dev,
+                    size_t workspace_bytes, void* stream);
+
+/* theta (raw) -> hyp (constrained) on the device: softplus (kernels.py:35,52).          */
+int bbo_gp_theta_to_hyp(int64_t d, int64_t batch, int32_t ard, int32_t has_scale,
+                        const double* theta_dev, double* hyp_dev, void* stream);
+
+/* ---- factorise: solve_gp_linear_system (objectives.py:20-31) ---------------------------
+ * For each problem computes, with np = bbo_padded_n(n):
+ *   linv  (batch, np, np)  L^-1, lower triangular, zero above the diagonal, identity
+ *                          on the padding (L = chol(K + noise I), lower)
+ *   alpha (batch, np)      K^-1 (y - c), zero on the padding      (`kinvy`)
+ *   chol  (batch, np, np)  L itself (lower triangle valid); may be NULL
+ *   logdet(batch)          sum_i log L_ii; may be NULL                                   */
+int bbo_gp_factorize(const bbo_gp_hyper* h, int64_t n, int64_t batch, const double* X_dev,
+                     const double* y_dev, const double* hyp_dev, double* linv_dev,
+                     double* alpha_dev, double* chol_dev, double* logdet_dev, int32_t* info_dev,
+                     void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---- fitted state used by predict / score (all dev pointers, one problem) ------------- */
+typedef struct bbo_gp_state {
+  bbo_gp_hyper h;
+  int64_t n;              /* observations */
+  const double* X;        /* (n, d) */
+  const double* hyp;      /* (2d+2) */
+  const double* linv;     /* (np, np) from bbo_gp_factorize */
+  const double* alpha;    /* (np) */
+  const float* linv_tf32; /* (np, np) float32 copy of linv rounded to TF32 (rna); only
+                             read when precision == BBO_PREC_TF32; see bbo_gp_make_tf32 */
+} bbo_gp_state;
+
+/* float32/TF32 copy of linv for the TF32 scoring mode */
+int bbo_gp_make_tf32(int64_t n, const double* linv_dev, float* linv_tf32_dev, void* stream);
+
+/* ---- posterior: GP.predict (gp.py:75-83) ------------------------------------------------
+ * Xq (q,d) dev -> mu[q], var[q] = k(x,x) - ||L^-1 k*||^2 + noise  (the diagonal of the
+ * reference's (q,q) result == its (q,1,d)-batched result).  If cov_full_dev != NULL the
+ * full (q,q) posterior covariance of gp.py:81-82 is written as well (q <= q_chunk).       */
+int bbo_gp_predict(const bbo_gp_state* st, const double* Xq_dev, int64_t q, double* mu_dev,
+                   double* var_dev, double* cov_full_dev, void* workspace_dev,
+                   size_t workspace_bytes, int64_t q_chunk, void* stream);
+
+/* ---- acquisition parameters (acquisitions.py:13-31) -------------------------------------- */
+typedef struct bbo_acq {
+  int32_t kind;    /* bbo_acq_kind */
+  int32_t _pad;
+  double best_f;   /* EI / PI incumbent (EI._best_f) */
+  double eps;      /* EI._eps, default 1e-6 */
+  double beta;     /* UCB.beta, default 1.8 */
+} bbo_acq;
+
+/* elementwise acquisition: out[i] = acq(mu[i], sigma[i]); is_f32 selects float/double.    */
+int bbo_acq_eval(const bbo_acq* a, const void* mu_dev, const void* sigma_dev, void* out_dev,
+                 int64_t count, int32_t is_f32, void* stream);
+
+/* ---- pool scoring + selection ----------------------------------------------------------------
+ * Scores q candidates and returns the k best (descending score, ties -> lowest index, the
+ * stable order of trial.py:289-294).  Xq: (q,d) dev, float64 when xq_is_f32 == 0 else float32.
+ * index_offset is added to every returned index (global index of this shard's first row).
+ * topk_score_dev[k] (float64) / topk_index_dev[k] (int64) receive the result; slots beyond
+ * the number of non-NaN candidates get score -inf and index -1.
+ * Optional full outputs (NULL to skip): mu_dev[q], var_dev[q], score_dev[q] (float64).
+ * nan_count_dev (int32, may be NULL) is incremented by the number of NaN scores (the
+ * reference raises ValueError on NaN, acquisitions.py:21 via Normal's arg validation).
+ * accumulate != 0: topk_* already hold a running top-k from earlier calls (other chunks of
+ * the same pool) and are merged with this call's candidates instead of being reset.        */
+int bbo_gp_score_pool(const bbo_gp_state* st, const bbo_acq* acq, int32_t precision,
+                      const void* Xq_dev, int32_t xq_is_f32, int64_t q, int64_t index_offset,
+                      int32_t k, double* topk_score_dev, int64_t* topk_index_dev, double* mu_dev,
+                      double* var_dev, double* score_dev, int32_t* nan_count_dev,
+                      void* workspace_dev, size_t workspace_bytes, int64_t q_chunk,
+                      int32_t accumulate, void* stream);
+
+/* Same with the candidate pool in HOST memory (pinned for full overlap).  The pool is
+ * streamed to the device in chunks of q_chunk rows on an internal copy stream, double
+ * buffered against the scoring kernels; staging_dev must hold 2*q_chunk*d elements of the
+ * candidate dtype.  topk_*_host receive the result; the call synchronises `stream`.       */
+int bbo_gp_score_pool_host(const bbo_gp_state* st, const bbo_acq* acq, int32_t precision,
+                           const void* Xq_host, int32_t xq_is_f32, int64_t q, int64_t index_offset,
+                           int32_t k, double* topk_score_host, int64_t* topk_index_host,
+                           void* staging_dev, double* topk_score_dev, int64_t* topk_index_dev,
+                           void* workspace_dev, size_t workspace_bytes, int64_t q_chunk,
+                           void* stream);
+
+/* Merge m (score,index) pairs (e.g. the all-gathered per-GPU top-k lists) into the k best,
+ * same ordering rule.  In-place safe when out != in.                                        */
+int bbo_topk_merge(const double* score_dev, const int64_t* index_dev, int64_t m, int32_t k,
+                   double* out_score_dev, int64_t* out_index_dev, void* stream);
+
+/* On-device uniform candidate generator (counter based, Philox4x32-10): fills out (q,d) with
+ * U[0,1) values that depend only on (seed, global row = row_offset + i, column), so any
+ * sharding of the pool produces the same candidates.  is_f32 selects float/double output.  */
+int bbo_pool_uniform(uint64_t seed, int64_t row_offset, int64_t q, int64_t d, void* out_dev,
+                     int32_t is_f32, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BBO_B200_H_ */
