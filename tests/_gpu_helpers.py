@@ -43,7 +43,8 @@ def synth_problem(seed, n, d, kind=O.RBF, noise=1e-4, ard=True, scale=True, ls_m
     X = rng.random((n, d))
     w = rng.standard_normal(d)
     y = np.sin(2.0 * X @ w) + 0.1 * rng.standard_normal(n)
-    y = (y - y.mean()) / (y.std(ddof=1) + 1e-6)
+    if n > 1:
+        y = (y - y.mean()) / (y.std(ddof=1) + 1e-6)
     raw_ls = rng.normal(ls_mean, 0.15, d) if ard else np.float64(ls_mean)
     p = O.GPParams(kind=kind, raw_lengthscale=raw_ls, raw_variance=(0.2 if scale else None), constant=0.05,
                    noise=noise, pairwise_eps=(1e-6 if kind == O.MATERN52 else 0.0))

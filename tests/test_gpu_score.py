@@ -43,8 +43,11 @@ def test_acquisitions_golden(cuda_device):
         assert ok.all(), (got[~ok], ref[~ok])
     got32 = np_(B.EI(best)(mu.float(), sd.float()))
     ref32 = a["ei_f32"]
-    m = np.isfinite(ref32) & (np.abs(ref32) > 1e-12)
-    np.testing.assert_allclose(got32[m], ref32[m], rtol=2e-4, atol=1e-9)
+    # float32: Phi = 0.5(1+erf) cancels in the tail, so the reference itself is only accurate to
+    # ~eps_f32 * max(sigma, |imp|) there -> mixed tolerance at float32 epsilon
+    m = np.isfinite(ref32)
+    tol32 = 2e-4 * np.abs(ref32) + 2.4e-7 * np.maximum(a["sd"], np.abs(a["mu"] - best))
+    assert (np.abs(got32[m] - ref32[m]) <= tol32[m]).all()
     with pytest.raises(ValueError):
         B.EI(best)(mu, sd * float("nan"))
     p = np_(B.PI(best)(mu[8:], sd[8:]))
@@ -136,9 +139,9 @@ def test_topk_ties_and_nan(cuda_device):
     Xq = np.concatenate([base, base, base])          # every score appears three times
     gp = gp_from_params(p, X, y)
     s, i, mu, var, sc = gp.score_pool(torch.as_tensor(Xq).cuda(), B.UCB(), 20, return_all=True)
-    assert (np_(i) < 50).all()
     order = np.lexsort((np.arange(150), -np_(sc)))[:20]
     np.testing.assert_array_equal(np_(i), order)
+    assert np_(i)[:3].tolist() == [np_(i)[0], np_(i)[0] + 50, np_(i)[0] + 100]   # tie -> ascending index
     s, i = gp.score_pool(torch.as_tensor(base[:3]).cuda(), B.UCB(), 8)
     assert (np_(i)[3:] == -1).all() and np.isneginf(np_(s)[3:]).all()
 
