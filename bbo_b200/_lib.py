@@ -51,6 +51,9 @@ _D = C.c_double
 SIGNATURES = {
     "bbo_version": (C.c_int, []),
     "bbo_last_cuda_error": (C.c_char_p, []),
+    "bbo_launch_count": (_I64, []),
+    "bbo_profile_enable": (None, [_I32]),
+    "bbo_profile_read": (C.c_int, [_I32, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "bbo_padded_n": (_I64, [_I64]),
     "bbo_gp_fit_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
     "bbo_gp_score_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I32]),
@@ -111,6 +114,16 @@ def require_cuda(device=None) -> torch.device:
     if dev.index is None:
         dev = torch.device("cuda", torch.cuda.current_device())
     return dev
+
+
+PROF_TAGS = {"vnorm": 0, "kstar": 1, "select": 2, "chol": 3, "trtri": 4, "grad": 5, "tf32": 6}
+
+
+def profile_read(tag: str):
+    """(regions, total_ms) of a profiled library region since the last read."""
+    n, ms = C.c_int64(0), C.c_double(0.0)
+    check(load().bbo_profile_read(PROF_TAGS[tag], C.byref(n), C.byref(ms)), "bbo_profile_read")
+    return n.value, ms.value
 
 
 def ptr(t):

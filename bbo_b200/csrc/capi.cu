@@ -1,5 +1,7 @@
 // extern "C" surface of libbbo_b200.so (see include/bbo_b200.h for the contract).
+#include <atomic>
 #include <string>
+#include <vector>
 
 #include "fit.cuh"
 #include "score.cuh"
@@ -9,6 +11,38 @@ static thread_local std::string g_last_error;
 int cuda_fail(cudaError_t e, const char* what) {
   g_last_error = std::string(cudaGetErrorName(e)) + ": " + cudaGetErrorString(e) + " at " + what;
   return BBO_ERR_CUDA;
+}
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct ProfState {
+  bool enabled = false;
+  std::vector<cudaEvent_t> ev[kProfTags];  // begin/end pairs
+  size_t used[kProfTags] = {0};
+};
+static ProfState g_prof;
+constexpr size_t kProfMaxEvents = 1 << 14;
+static cudaEvent_t prof_event(int tag) {
+  auto& v = g_prof.ev[tag];
+  if (g_prof.used[tag] >= kProfMaxEvents) return nullptr;
+  if (g_prof.used[tag] >= v.size()) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    v.push_back(e);
+  }
+  return v[g_prof.used[tag]++];
+}
+void prof_begin(int tag, cudaStream_t st) {
+  if (!g_prof.enabled) return;
+  if (g_prof.used[tag] + 2 > kProfMaxEvents) return;
+  cudaEvent_t e = prof_event(tag);
+  if (e) cudaEventRecord(e, st);
+}
+void prof_end(int tag, cudaStream_t st) {
+  if (!g_prof.enabled) return;
+  if ((g_prof.used[tag] & 1) == 0) return;  // no matching begin
+  cudaEvent_t e = prof_event(tag);
+  if (e) cudaEventRecord(e, st);
 }
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 static bool hyper_ok(const bbo_gp_hyper* h) {
@@ -22,6 +56,28 @@ using namespace bbo;
 extern "C" {
 
 int bbo_version(void) { return 100; }
+int64_t bbo_launch_count(void) { return g_launches.load(); }
+void bbo_profile_enable(int32_t on) {
+  g_prof.enabled = on != 0;
+  for (int t = 0; t < kProfTags; ++t) g_prof.used[t] = 0;
+}
+int bbo_profile_read(int32_t tag, int64_t* regions, double* total_ms) {
+  if (tag < 0 || tag >= kProfTags || !regions || !total_ms) return BBO_ERR_BAD_ARG;
+  BBO_CUDA_CHECK(cudaDeviceSynchronize());
+  double tot = 0.0;
+  int64_t n = 0;
+  for (size_t i = 0; i + 1 < g_prof.used[tag]; i += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_prof.ev[tag][i], g_prof.ev[tag][i + 1]) == cudaSuccess) {
+      tot += ms;
+      ++n;
+    }
+  }
+  g_prof.used[tag] = 0;
+  *regions = n;
+  *total_ms = tot;
+  return BBO_OK;
+}
 const char* bbo_last_cuda_error(void) { return g_last_error.c_str(); }
 int64_t bbo_padded_n(int64_t n) { return padded(n); }
 

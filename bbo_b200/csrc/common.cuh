@@ -23,7 +23,27 @@ int cuda_fail(cudaError_t e, const char* what);
     cudaError_t _e = (expr);                                    \
     if (_e != cudaSuccess) return ::bbo::cuda_fail(_e, #expr);  \
   } while (0)
-#define BBO_LAUNCH_CHECK() BBO_CUDA_CHECK(cudaGetLastError())
+// every kernel launch goes through this: counts launches (bbo_launch_count) and checks errors
+void count_launch();
+#define BBO_LAUNCH_CHECK()               \
+  do {                                   \
+    ::bbo::count_launch();               \
+    BBO_CUDA_CHECK(cudaGetLastError());  \
+  } while (0)
+
+// optional per-region device timing with CUDA events on the launching stream (bbo_profile_*)
+enum ProfTag {
+  kProfVnorm = 0,   // FP64 posterior-variance panel (k_vnorm)
+  kProfKstar = 1,   // cross-covariance + mean (k_kstar)
+  kProfSelect = 2,  // acquisition epilogue + top-k
+  kProfChol = 3,    // covariance build + blocked Cholesky
+  kProfTrtri = 4,   // triangular inverse + solves
+  kProfGrad = 5,    // LAUUM + gradient reduction (+ Adam)
+  kProfTf32 = 6,    // TF32 scoring panel (tcgen05)
+  kProfTags = 8
+};
+void prof_begin(int tag, cudaStream_t st);
+void prof_end(int tag, cudaStream_t st);
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {

@@ -423,6 +423,7 @@ static int posterior_chunk(const bbo_gp_state& s, const ScoreWorkspace& w, int p
   }
   const int nsplit = pick_nsplit(qc_pad, w.np);
   *nsplit_out = nsplit;
+  prof_begin(kProfKstar, st);
   if (xq_is_f32)
     k_kstar<float><<<unsigned(qc_pad / 64), 256, 0, st>>>(s.h, static_cast<const float*>(Xq), qc, s.X, s.n, w.np,
                                                          s.hyp, s.alpha, w.Ks, w.mu);
@@ -430,9 +431,12 @@ static int posterior_chunk(const bbo_gp_state& s, const ScoreWorkspace& w, int p
     k_kstar<double><<<unsigned(qc_pad / 64), 256, 0, st>>>(s.h, static_cast<const double*>(Xq), qc, s.X, s.n,
                                                           w.np, s.hyp, s.alpha, w.Ks, w.mu);
   BBO_LAUNCH_CHECK();
+  prof_end(kProfKstar, st);
+  prof_begin(kProfVnorm, st);
   k_vnorm<<<dim3(unsigned(qc_pad / 128), unsigned(nsplit)), Cfg128x64::THREADS, Cfg128x64::SMEM_BYTES, st>>>(
       w.Ks, s.linv, w.np, w.qp, w.vpart);
   BBO_LAUNCH_CHECK();
+  prof_end(kProfVnorm, st);
   return BBO_OK;
 }
 
@@ -497,6 +501,7 @@ int gp_score_pool(const bbo_gp_state& s, const bbo_acq& acq, int precision, cons
     int nsplit = 1;
     rc = posterior_chunk(s, w, precision, xq, xq_is_f32, qc, &nsplit, st);
     if (rc != BBO_OK) return rc;
+    prof_begin(kProfSelect, st);
     k_acq<<<unsigned(ceil_div(qc, 256)), 256, 0, st>>>(
         s.h, acq, 1, precision == BBO_PREC_TF32, s.hyp, w.mu, w.vpart, nsplit, w.qp, qc, w.score,
         mu_out ? mu_out + c0 : nullptr, var_out ? var_out + c0 : nullptr, score_out ? score_out + c0 : nullptr,
@@ -510,6 +515,7 @@ int gp_score_pool(const bbo_gp_state& s, const bbo_acq& acq, int precision, cons
     BBO_LAUNCH_CHECK();
     rc = topk_levels(w.la_s, w.la_i, (nb + 1) * k, w.lb_s, w.lb_i, k, topk_s, topk_i, st);
     if (rc != BBO_OK) return rc;
+    prof_end(kProfSelect, st);
   }
   return BBO_OK;
 }

@@ -254,6 +254,14 @@ class CudaGP(Surrogate):
     def state(self):
         return self._ensure_state()
 
+    def install_state(self, hyp: torch.Tensor, linv: torch.Tensor, alpha: torch.Tensor) -> None:
+        """Adopt a fitted state computed elsewhere (e.g. broadcast from the fitting GPU)."""
+        if linv.shape != (self.np, self.np) or alpha.shape != (self.np,) or hyp.shape != (2 * self.d + 2,):
+            raise ValueError("state tensors have the wrong shape")
+        st = _lib.GpState(h=self._hyper(), n=self.n, X=self._X.data_ptr(), hyp=hyp.data_ptr(),
+                          linv=linv.data_ptr(), alpha=alpha.data_ptr(), linv_tf32=None)
+        self._state = {"st": st, "hyp": hyp, "linv": linv, "alpha": alpha, "logdet": None, "linv_tf32": None}
+
     # ------------------------------------------------------------------ predict
     def predict_diag(self, query_X: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """Per-candidate posterior mean and variance, float64 (q,), (q,)."""

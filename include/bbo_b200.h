@@ -72,6 +72,16 @@ typedef enum bbo_precision { BBO_PREC_FP64 = 0, BBO_PREC_TF32 = 1 } bbo_precisio
 int bbo_version(void);
 /* text of the last CUDA error seen by this thread ("" if none) */
 const char* bbo_last_cuda_error(void);
+/* number of CUDA kernels this library has launched in this process (cumulative) */
+int64_t bbo_launch_count(void);
+/* Optional device-side timing of library regions with CUDA events recorded on the launching
+ * stream.  enable(1) clears the counters; read() synchronises the device, returns how many
+ * regions of `tag` ran and their summed duration, and clears that tag.
+ * tags: 0 FP64 variance panel (k_vnorm), 1 cross-covariance+mean (k_kstar), 2 acquisition+top-k,
+ *       3 covariance build + Cholesky, 4 triangular inverse + solves, 5 LAUUM + gradient (+Adam),
+ *       6 TF32 scoring panel.                                                              */
+void bbo_profile_enable(int32_t on);
+int bbo_profile_read(int32_t tag, int64_t* regions, double* total_ms);
 /* n rounded up to BBO_ROW_ALIGN */
 int64_t bbo_padded_n(int64_t n);
 
