@@ -55,6 +55,7 @@ SIGNATURES = {
     "bbo_profile_enable": (None, [_I32]),
     "bbo_profile_read": (C.c_int, [_I32, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "bbo_padded_n": (_I64, [_I64]),
+    "bbo_tf32_rows": (_I64, [_I64]),
     "bbo_gp_fit_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
     "bbo_gp_score_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I32]),
     "bbo_gp_predict_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I32]),

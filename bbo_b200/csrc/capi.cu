@@ -80,6 +80,7 @@ int bbo_profile_read(int32_t tag, int64_t* regions, double* total_ms) {
 }
 const char* bbo_last_cuda_error(void) { return g_last_error.c_str(); }
 int64_t bbo_padded_n(int64_t n) { return padded(n); }
+int64_t bbo_tf32_rows(int64_t n) { return tf32_rows(n); }
 
 size_t bbo_gp_fit_workspace_bytes(int64_t n, int64_t d, int64_t batch) {
   if (n < 1 || d < 1 || batch < 1) return 0;

@@ -417,10 +417,7 @@ static int set_smem_attrs() {
 static int posterior_chunk(const bbo_gp_state& s, const ScoreWorkspace& w, int precision, const void* Xq,
                            int xq_is_f32, int64_t qc, int* nsplit_out, cudaStream_t st) {
   const int64_t qc_pad = ceil_div(qc, 128) * 128;
-  if (precision == BBO_PREC_TF32) {
-    *nsplit_out = 1;
-    return score_tf32_chunk(s, w, Xq, xq_is_f32, qc, qc_pad, st);
-  }
+  if (precision == BBO_PREC_TF32) return score_tf32_chunk(s, w, Xq, xq_is_f32, qc, qc_pad, nsplit_out, st);
   const int nsplit = pick_nsplit(qc_pad, w.np);
   *nsplit_out = nsplit;
   prof_begin(kProfKstar, st);

@@ -35,8 +35,9 @@ int topk_merge(const double* score, const int64_t* index, int64_t m, int k, doub
 // TF32 mode (score_tf32.cu): fills w.mu and w.vpart[0, :] for one chunk
 size_t score_tf32_extra_bytes(int64_t n, int64_t d, int64_t qp);
 int score_tf32_chunk(const bbo_gp_state& s, const ScoreWorkspace& w, const void* Xq, int xq_is_f32, int64_t qc,
-                     int64_t qc_pad, cudaStream_t st);
+                     int64_t qc_pad, int* nsplit_out, cudaStream_t st);
 int make_tf32(int64_t n, const double* linv, float* out, cudaStream_t st);
+int64_t tf32_rows(int64_t n);
 
 int pool_uniform(uint64_t seed, int64_t row_offset, int64_t q, int64_t d, void* out, int is_f32, cudaStream_t st);
 

@@ -1,29 +1,446 @@
-// TF32 scoring mode (tcgen05 panel) -- placeholder until the tcgen05 pipeline lands.
+// TF32 scoring mode: the n^2 posterior-variance panel on 5th-gen tensor cores.
+//
+//   |L^-1 k*_c|^2 = sum_i ( sum_{j<=i} Ks[c,j] * Linv[i,j] )^2          (gp.py:80-81)
+//
+// k_kstar_f32     K* in FP32 exact-difference form (kernel_impl.py:80-96), rounded to TF32 with
+//                 cvt.rna (round-to-nearest: unbiased, unlike the tensor core's own truncation),
+//                 fused with mu = c + K* alpha.
+// k_vnorm_tf32    warp-specialised tcgen05 GEMM, one CTA per SM:
+//                   warp 0   TMA producer: cp.async.bulk.tensor.2d (128B swizzle) of a 128x32 K* tile
+//                            and a 256x32 L^-1 tile per stage, 4-stage mbarrier ring (192 KB smem)
+//                   warp 1   MMA issuer: one thread, tcgen05.mma.cta_group::1.kind::tf32, M=128 (candidates)
+//                            x N=256 (rows of L^-1) x K=8, accumulators in TMEM (2 x 256 columns, double
+//                            buffered against the epilogue); tcgen05.commit releases smem stages / publishes
+//                            the accumulator
+//                   warps 2-5 epilogue: tcgen05.ld.32x32b.x32 TMEM -> registers, square + row-sum;
+//                            V = L^-1 k* is never written anywhere.
+//                 Triangular: row block nb only contracts k < (nb+1)*256.
+// SASS evidence: UTCHMMA / UTMALDG / LDTM / SYNCS (see profiles/).
+#include <cuda.h>
+
 #include "score.cuh"
 
 namespace bbo {
 
-size_t score_tf32_extra_bytes(int64_t, int64_t, int64_t) { return 0; }
+namespace tf {
+constexpr int BM = 128;       // candidates per CTA tile (UMMA M)
+constexpr int BN = 256;       // rows of L^-1 per accumulator (UMMA N)
+constexpr int BK = 32;        // floats per stage row = 128 bytes = one swizzle atom
+constexpr int UK = 8;         // UMMA K for tf32
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 4;   // 16 KB
+constexpr int B_BYTES = BN * BK * 4;   // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;   // + slack for 1024-byte alignment
+constexpr int THREADS = 192;  // 6 warps
+constexpr int TMEM_COLS = 512;
 
-int score_tf32_chunk(const bbo_gp_state&, const ScoreWorkspace&, const void*, int, int64_t, int64_t,
-                     cudaStream_t) {
-  return BBO_ERR_BAD_ARG;
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: a protocol bug traps (-> CUDA error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  uint64_t t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((spin & 1023u) == 1023u) {   // time-based bound: 2 s without progress -> trap
+      uint64_t t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 2000000000ull) asm volatile("trap;");
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major operand tile, rows of 128 bytes, 128-byte swizzle (what TMA SWIZZLE_128B writes):
+// start address >> 4, LBO = 1 (unused for swizzled K-major), SBO = 1024 B (8 rows), version 1, layout 2
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= uint64_t((saddr & 0x3FFFFu) >> 4);
+  d |= uint64_t(1) << 16;
+  d |= uint64_t(1024 >> 4) << 32;
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(2) << 61;
+  return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+}  // namespace tf
+
+// ------------------------------------------------------------------------------------------
+// vpart[split, c] = sum over this split's 256-row blocks of (Ks[c,:] . Linv[i,:])^2
+// grid (qc_pad/128, nsplit), 192 threads, 1 CTA / SM.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(tf::THREADS, 1)
+k_vnorm_tf32(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int np,
+             int64_t qc_pad, double* __restrict__ vpart) {
+  using namespace tf;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_base_sh;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;   // 1024-byte aligned tile ring
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  const int c0 = blockIdx.x * BM;
+  const int nblk = (np + BN - 1) / BN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {   // TMEM allocation: one warp, all 512 columns (1 CTA per SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_sh;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int nb = blockIdx.y; nb < nblk; nb += gridDim.y) {
+        const int kend = min((nb + 1) * BN, np);
+        for (int k = 0; k < kend; k += BK) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = sgen + stage * STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          tma_load_2d(sa, &mapA, &full_bar[stage], k, c0);
+          tma_load_2d(sa + A_BYTES, &mapB, &full_bar[stage], k, nb * BN);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=tf32, both K-major, N=256, M=128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int nb = blockIdx.y; nb < nblk; nb += gridDim.y) {
+        const int kend = min((nb + 1) * BN, np);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
+        for (int k = 0; k < kend; k += BK) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = sbase + stage * STAGE_BYTES;
+          const uint64_t adesc = make_desc(sa), bdesc = make_desc(sa + A_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < BK / UK; ++kk) {
+            // advance 32 bytes (8 tf32) inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+            tc_mma_tf32(d_tmem, adesc + uint64_t(kk * 2), bdesc + uint64_t(kk * 2), idesc, (k | kk) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);   // frees the smem stage once these MMAs have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit(&tfull_bar[acc]);       // accumulator complete
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;                // candidate row within the tile
+    double total = 0.0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int nb = blockIdx.y; nb < nblk; nb += gridDim.y) {
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN);
+      float part = 0.f;
+#pragma unroll 2
+      for (int c = 0; c < BN; c += 32) {
+        float v[32];
+        tmem_ld32(taddr + uint32_t(c), v);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          s0 = fmaf(v[i], v[i], s0);
+          s1 = fmaf(v[i + 1], v[i + 1], s1);
+          s2 = fmaf(v[i + 2], v[i + 2], s2);
+          s3 = fmaf(v[i + 3], v[i + 3], s3);
+        }
+        part += (s0 + s1) + (s2 + s3);
+      }
+      total += double(part);
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    vpart[int64_t(blockIdx.y) * qc_pad + c0 + row] = total;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
 }
 
-__global__ void k_make_tf32(int64_t total, const double* __restrict__ in, float* __restrict__ out) {
+// ------------------------------------------------------------------------------------------
+// K* (qc_pad, np) float32 (TF32-rounded) and mu.  grid (qc_pad/64), 256 threads.
+// ------------------------------------------------------------------------------------------
+constexpr int kFC = 32, kFS = kFC + 1;
+
+template <typename T1>
+__global__ void __launch_bounds__(256)
+k_kstar_f32(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const double* __restrict__ X, int64_t n,
+            int64_t np, const double* __restrict__ hyp, const double* __restrict__ alpha, float* __restrict__ Ks,
+            double* __restrict__ mu) {
+  __shared__ float x1s[64 * kFS], x2s[64 * kFS], ils[kFC];
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int64_t c0 = int64_t(blockIdx.x) * 64;
+  const int d = h.d;
+  const bool matern = h.kind == BBO_KERNEL_MATERN52;
+  const float eps = matern ? float(h.pairwise_eps) : 0.f;
+  const float s2 = float(hyp[2 * d]);
+  float macc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t j0 = 0; j0 < np; j0 += 64) {
+    float s[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) s[a][b] = 0.f;
+    for (int kc = 0; kc < d; kc += kFC) {
+      const int kw = min(kFC, d - kc);
+      __syncthreads();
+      for (int idx = tid; idx < 64 * kFC; idx += 256) {
+        int r = idx / kFC, k = idx % kFC;
+        float v1 = 0.f, v2 = 0.f;
+        if (k < kw) {
+          if (c0 + r < qc) v1 = float(Xq[(c0 + r) * d + kc + k]);
+          if (j0 + r < n) v2 = float(X[(j0 + r) * d + kc + k]);
+        }
+        x1s[r * kFS + k] = v1;
+        x2s[r * kFS + k] = v2;
+      }
+      if (tid < kFC) ils[tid] = tid < kw ? float(hyp[d + kc + tid]) : 0.f;
+      __syncthreads();
+      for (int k = 0; k < kw; ++k) {
+        const float il = ils[k];
+        float av[4], bv[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) av[a] = x1s[(ty * 4 + a) * kFS + k];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) bv[b] = x2s[(tx + 16 * b) * kFS + k];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            float de = fmaf(bv[b] - av[a], il, eps);
+            s[a][b] = fmaf(de, de, s[a][b]);
+          }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int64_t j = j0 + tx + 16 * b;
+        float v = 0.f;
+        if (j < n) {
+          if (matern) {
+            float r = 2.2360679775f * sqrtf(s[a][b]);
+            v = s2 * (1.f + r + r * r * (1.f / 3.f)) * __expf(-r);
+          } else {
+            v = s2 * __expf(-0.5f * s[a][b]);
+          }
+        }
+        macc[a] = fmaf(v, float(alpha[j]), macc[a]);
+        uint32_t u;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+        Ks[(c0 + ty * 4 + a) * np + j] = __uint_as_float(u);
+      }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    float v = macc[a];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (tx == 0) mu[c0 + ty * 4 + a] = hyp[2 * d + 1] + double(v);
+  }
+}
+
+// out (rows256, np): TF32-rounded copy of linv (np, np); rows >= np are zero so that every
+// 256-row TMA box of the B operand is fully in bounds.
+__global__ void k_make_tf32(int64_t valid, int64_t total, const double* __restrict__ in, float* __restrict__ out) {
   int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < total) {
-    float f = static_cast<float>(in[i]);
+    float f = i < valid ? static_cast<float>(in[i]) : 0.f;
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(f));
     out[i] = __uint_as_float(u);
   }
 }
 
+int64_t tf32_rows(int64_t n) { return ceil_div(padded(n), tf::BN) * tf::BN; }
+
 int make_tf32(int64_t n, const double* linv, float* out, cudaStream_t st) {
-  const int64_t np = padded(n), total = np * np;
-  k_make_tf32<<<unsigned(ceil_div(total, 256)), 256, 0, st>>>(total, linv, out);
+  const int64_t np = padded(n), valid = np * np, total = tf32_rows(n) * np;
+  k_make_tf32<<<unsigned(ceil_div(total, 256)), 256, 0, st>>>(valid, total, linv, out);
   BBO_LAUNCH_CHECK();
+  return BBO_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+size_t score_tf32_extra_bytes(int64_t n, int64_t, int64_t qp) {
+  return size_t(qp) * size_t(padded(n)) * sizeof(float) + 256;   // float32 K* chunk
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// 2-D float32 row-major (rows, cols) tensor, box = (box_rows, 32 floats), 128-byte swizzle
+static int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return cuda_fail(cudaErrorNotSupported, "cudaGetDriverEntryPoint(cuTensorMapEncodeTiled)");
+  cuuint64_t gdim[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+  cuuint64_t gstr[1] = {cuuint64_t(cols) * sizeof(float)};
+  cuuint32_t box[2] = {cuuint32_t(tf::BK), cuuint32_t(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return cuda_fail(cudaErrorInvalidValue, "cuTensorMapEncodeTiled");
+  return BBO_OK;
+}
+
+int score_tf32_chunk(const bbo_gp_state& s, const ScoreWorkspace& w, const void* Xq, int xq_is_f32, int64_t qc,
+                     int64_t qc_pad, int* nsplit_out, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    BBO_CUDA_CHECK(cudaFuncSetAttribute(k_vnorm_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, tf::SMEM_BYTES));
+    attr_done = true;
+  }
+  float* Ks = static_cast<float*>(w.tf32);
+  const int64_t np = w.np;
+  prof_begin(kProfKstar, st);
+  if (xq_is_f32)
+    k_kstar_f32<float><<<unsigned(qc_pad / 64), 256, 0, st>>>(s.h, static_cast<const float*>(Xq), qc, s.X, s.n, np,
+                                                             s.hyp, s.alpha, Ks, w.mu);
+  else
+    k_kstar_f32<double><<<unsigned(qc_pad / 64), 256, 0, st>>>(s.h, static_cast<const double*>(Xq), qc, s.X, s.n,
+                                                              np, s.hyp, s.alpha, Ks, w.mu);
+  BBO_LAUNCH_CHECK();
+  prof_end(kProfKstar, st);
+
+  CUtensorMap mapA, mapB;
+  int rc = make_map(&mapA, Ks, qc_pad, np, tf::BM);
+  if (rc != BBO_OK) return rc;
+  rc = make_map(&mapB, s.linv_tf32, tf32_rows(s.n), np, tf::BN);
+  if (rc != BBO_OK) return rc;
+  const int64_t tiles = qc_pad / tf::BM;
+  const int64_t nblk = ceil_div(np, tf::BN);
+  int64_t nsplit = ceil_div(148, tiles);          // fill the 148 SMs when the chunk is small
+  if (nsplit > nblk) nsplit = nblk;
+  if (nsplit > kMaxSplit) nsplit = kMaxSplit;
+  if (nsplit < 1) nsplit = 1;
+  *nsplit_out = int(nsplit);
+  prof_begin(kProfTf32, st);
+  k_vnorm_tf32<<<dim3(unsigned(tiles), unsigned(nsplit)), tf::THREADS, tf::SMEM_BYTES, st>>>(mapA, mapB, int(np),
+                                                                                            w.qp, w.vpart);
+  BBO_LAUNCH_CHECK();
+  prof_end(kProfTf32, st);
   return BBO_OK;
 }
 

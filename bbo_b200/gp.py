@@ -134,6 +134,7 @@ class CudaGP(Surrogate):
         if self._theta.ard and self._theta.n_ls != self.d:
             raise ValueError(f"ARD lengthscale has {self._theta.n_ls} dims, X has {self.d}")
         self._q_chunk = int(q_chunk) if q_chunk else default_q_chunk(self.n)
+        self._q_chunk_auto = not q_chunk
         self._state = None           # (GpState, keep-alive tensors)
         self._ws = {}                # workspace cache
         self.last_values = None      # objective value seen at each epoch of the last train()
@@ -243,7 +244,8 @@ class CudaGP(Surrogate):
                                "linv_tf32": None}
         if want_tf32 and self._state["linv_tf32"] is None:
             with torch.cuda.device(self._device):
-                lt = torch.empty(self.np, self.np, dtype=torch.float32, device=self._device)
+                lt = torch.empty(int(self._lib.bbo_tf32_rows(self.n)), self.np, dtype=torch.float32,
+                                 device=self._device)
                 _lib.check(self._lib.bbo_gp_make_tf32(self.n, _lib.ptr(self._state["linv"]), _lib.ptr(lt),
                                                       _lib.stream_ptr(self._device)), "bbo_gp_make_tf32")
                 self._state["linv_tf32"] = lt
@@ -338,6 +340,9 @@ class CudaGP(Surrogate):
         q = Xq.shape[0]
         with torch.cuda.device(self._device):
             qc = min(self._q_chunk, max(128, (q + 127) // 128 * 128))
+            if prec == _lib.PREC_TF32 and q >= 148 * 128 and self._q_chunk_auto:
+                # one 128-candidate tile per SM and per wave: chunks of 148 x 128 candidates
+                qc = min(q // (148 * 128), max(1, (768 << 20) // (148 * 128 * self.np * 4))) * 148 * 128
             ws = self._workspace("score%d" % prec,
                                  int(self._lib.bbo_gp_score_workspace_bytes(self.n, self.d, qc, prec)))
             if running is not None:

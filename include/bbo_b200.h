@@ -170,11 +170,14 @@ typedef struct bbo_gp_state {
   const double* hyp;      /* (2d+2) */
   const double* linv;     /* (np, np) from bbo_gp_factorize */
   const double* alpha;    /* (np) */
-  const float* linv_tf32; /* (np, np) float32 copy of linv rounded to TF32 (rna); only
+  const float* linv_tf32; /* (bbo_tf32_rows(n), np) float32 copy of linv rounded to TF32; only
                              read when precision == BBO_PREC_TF32; see bbo_gp_make_tf32 */
 } bbo_gp_state;
 
-/* float32/TF32 copy of linv for the TF32 scoring mode */
+/* float32 copy of linv rounded to TF32 (round-to-nearest) for the TF32 scoring mode:
+ * linv_tf32_dev is (bbo_tf32_rows(n), np) -- np rows of data followed by zero rows up to a
+ * multiple of 256, so that every TMA box of the tensor-core panel is in bounds.           */
+int64_t bbo_tf32_rows(int64_t n);
 int bbo_gp_make_tf32(int64_t n, const double* linv_dev, float* linv_tf32_dev, void* stream);
 
 /* ---- posterior: GP.predict (gp.py:75-83) ------------------------------------------------
