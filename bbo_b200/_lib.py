@@ -21,6 +21,7 @@ ACQ_EI, ACQ_UCB, ACQ_PI = 0, 1, 2
 PREC_FP64, PREC_TF32 = 0, 1
 ROW_ALIGN = 128
 TOPK_MAX = 128
+HOST_STAGE_CHUNKS = 4
 
 
 class GpHyper(C.Structure):

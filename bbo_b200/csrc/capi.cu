@@ -206,7 +206,9 @@ int bbo_gp_score_pool_host(const bbo_gp_state* st, const bbo_acq* acq, int32_t p
     return BBO_ERR_BAD_ARG;
   cudaStream_t cs = S(stream), copy = nullptr;
   cudaEvent_t ready[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
-  const int64_t qp = (q_chunk < 128 ? 128 : (q_chunk + 127) / 128 * 128);
+  // one staging buffer = BBO_HOST_STAGE_CHUNKS scoring chunks, so that the K*/panel pipeline inside
+  // gp_score_pool has several chunks to overlap
+  const int64_t qp = BBO_HOST_STAGE_CHUNKS * (q_chunk < 128 ? 128 : (q_chunk + 127) / 128 * 128);
   const size_t esz = xq_is_f32 ? sizeof(float) : sizeof(double);
   const size_t row = size_t(st->h.d) * esz;
   int rc = BBO_OK;

@@ -361,7 +361,8 @@ static int pick_nsplit(int64_t qc_pad, int64_t np) {
 size_t ScoreWorkspace::bytes(int64_t n, int64_t d, int64_t q_chunk, int precision, bool want_full) {
   const int64_t np = padded(n), qp = round_chunk(q_chunk);
   const int64_t nblk = ceil_div(qp, kSeg);
-  size_t doubles = size_t(qp) * np * (want_full ? 2 : 1)  // Ks (+V)
+  const size_t ks = (precision == BBO_PREC_TF32 && !want_full) ? 0 : size_t(qp) * np;   // TF32 keeps K* in float32
+  size_t doubles = ks * (want_full ? 2 : 1)  // Ks (+V)
                    + size_t(kMaxSplit) * qp + 2 * size_t(qp)  // vpart, mu, score
                    + 2 * size_t(BBO_TOPK_MAX) * (nblk + 1) * 2;  // two (score,index) ping-pong lists
   size_t extra = 0;
@@ -377,7 +378,7 @@ int ScoreWorkspace::bind(void* ws, size_t ws_bytes, int64_t n, int64_t d, int64_
   uintptr_t p = (reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255);
   double* q = reinterpret_cast<double*>(p);
   Ks = q;
-  q += size_t(qp) * np;
+  if (!(precision == BBO_PREC_TF32 && !want_full)) q += size_t(qp) * np;
   V = want_full ? q : nullptr;
   if (want_full) q += size_t(qp) * np;
   vpart = q;
@@ -417,7 +418,7 @@ static int set_smem_attrs() {
 static int posterior_chunk(const bbo_gp_state& s, const ScoreWorkspace& w, int precision, const void* Xq,
                            int xq_is_f32, int64_t qc, int* nsplit_out, cudaStream_t st) {
   const int64_t qc_pad = ceil_div(qc, 128) * 128;
-  if (precision == BBO_PREC_TF32) return score_tf32_chunk(s, w, Xq, xq_is_f32, qc, qc_pad, nsplit_out, st);
+  if (precision != BBO_PREC_FP64) return BBO_ERR_BAD_ARG;
   const int nsplit = pick_nsplit(qc_pad, w.np);
   *nsplit_out = nsplit;
   prof_begin(kProfKstar, st);
@@ -491,16 +492,11 @@ int gp_score_pool(const bbo_gp_state& s, const bbo_acq& acq, int precision, cons
     k_topk_init<<<1, BBO_TOPK_MAX, 0, st>>>(topk_s, topk_i, k);
     BBO_LAUNCH_CHECK();
   }
-  const size_t esz = xq_is_f32 ? sizeof(float) : sizeof(double);
-  for (int64_t c0 = 0; c0 < q; c0 += w.qp) {
-    const int64_t qc = (q - c0 < w.qp) ? q - c0 : w.qp;
-    const void* xq = static_cast<const char*>(Xq) + size_t(c0) * s.h.d * esz;
-    int nsplit = 1;
-    rc = posterior_chunk(s, w, precision, xq, xq_is_f32, qc, &nsplit, st);
-    if (rc != BBO_OK) return rc;
+  // acquisition + running top-k of one finished chunk (mu and |v|^2 partials are ready on st)
+  auto consume = [&](int64_t c0, int64_t qc, const double* mu_chunk, int nsplit) -> int {
     prof_begin(kProfSelect, st);
     k_acq<<<unsigned(ceil_div(qc, 256)), 256, 0, st>>>(
-        s.h, acq, 1, precision == BBO_PREC_TF32, s.hyp, w.mu, w.vpart, nsplit, w.qp, qc, w.score,
+        s.h, acq, 1, precision == BBO_PREC_TF32, s.hyp, mu_chunk, w.vpart, nsplit, w.qp, qc, w.score,
         mu_out ? mu_out + c0 : nullptr, var_out ? var_out + c0 : nullptr, score_out ? score_out + c0 : nullptr,
         nan_count);
     BBO_LAUNCH_CHECK();
@@ -510,9 +506,21 @@ int gp_score_pool(const bbo_gp_state& s, const bbo_acq& acq, int precision, cons
     BBO_CUDA_CHECK(cudaMemcpyAsync(w.la_i, topk_i, size_t(k) * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
     k_topk_seg<<<unsigned(nb), 256, 0, st>>>(w.score, nullptr, index_offset + c0, qc, k, w.la_s + k, w.la_i + k);
     BBO_LAUNCH_CHECK();
-    rc = topk_levels(w.la_s, w.la_i, (nb + 1) * k, w.lb_s, w.lb_i, k, topk_s, topk_i, st);
-    if (rc != BBO_OK) return rc;
+    int rc2 = topk_levels(w.la_s, w.la_i, (nb + 1) * k, w.lb_s, w.lb_i, k, topk_s, topk_i, st);
+    if (rc2 != BBO_OK) return rc2;
     prof_end(kProfSelect, st);
+    return BBO_OK;
+  };
+  if (precision == BBO_PREC_TF32) return q == 0 ? BBO_OK : score_tf32_pipeline(s, w, Xq, xq_is_f32, q, consume, st);
+  const size_t esz = xq_is_f32 ? sizeof(float) : sizeof(double);
+  for (int64_t c0 = 0; c0 < q; c0 += w.qp) {
+    const int64_t qc = (q - c0 < w.qp) ? q - c0 : w.qp;
+    const void* xq = static_cast<const char*>(Xq) + size_t(c0) * s.h.d * esz;
+    int nsplit = 1;
+    rc = posterior_chunk(s, w, precision, xq, xq_is_f32, qc, &nsplit, st);
+    if (rc != BBO_OK) return rc;
+    rc = consume(c0, qc, w.mu, nsplit);
+    if (rc != BBO_OK) return rc;
   }
   return BBO_OK;
 }

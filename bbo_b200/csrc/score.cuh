@@ -1,5 +1,7 @@
 // Host-side declarations of the scoring path (score.cu, score_tf32.cu).
 #pragma once
+#include <functional>
+
 #include "common.cuh"
 
 namespace bbo {
@@ -32,10 +34,11 @@ int acq_eval(const bbo_acq& a, const void* mu, const void* sd, void* out, int64_
 int topk_merge(const double* score, const int64_t* index, int64_t m, int k, double* out_s, int64_t* out_i,
                cudaStream_t st);
 
-// TF32 mode (score_tf32.cu): fills w.mu and w.vpart[0, :] for one chunk
+// TF32 mode (score_tf32.cu): pipelined K* (aux stream) / tcgen05 panel (st) over all chunks of a pool;
+// consume(chunk_start, qc, mu, nsplit) enqueues the per-chunk acquisition / selection work on st.
 size_t score_tf32_extra_bytes(int64_t n, int64_t d, int64_t qp);
-int score_tf32_chunk(const bbo_gp_state& s, const ScoreWorkspace& w, const void* Xq, int xq_is_f32, int64_t qc,
-                     int64_t qc_pad, int* nsplit_out, cudaStream_t st);
+int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const void* Xq, int xq_is_f32, int64_t q,
+                        const std::function<int(int64_t, int64_t, const double*, int)>& consume, cudaStream_t st);
 int make_tf32(int64_t n, const double* linv, float* out, cudaStream_t st);
 int64_t tf32_rows(int64_t n);
 

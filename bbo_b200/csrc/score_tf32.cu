@@ -18,6 +18,9 @@
 // SASS evidence: UTCHMMA / UTMALDG / LDTM / SYNCS (see profiles/).
 #include <cuda.h>
 
+#include <cstdlib>
+#include <functional>
+
 #include "score.cuh"
 
 namespace bbo {
@@ -346,6 +349,163 @@ k_kstar_f32(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const double*
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Pre-scaled float32 training set for the fast K* kernel: Xs[j,k] = float(X[j,k] / l_k) (scaled in
+// float64, rounded once), zero rows on the padding; bnorm[j] = |Xs[j,:]|^2; alpha32 = float(alpha).
+// grid (np/8), 256 threads: one warp per training row.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_prescale(const double* __restrict__ X, int64_t n, int64_t np, int d, const double* __restrict__ hyp,
+           const double* __restrict__ alpha, float* __restrict__ Xs, float* __restrict__ bnorm,
+           float* __restrict__ alpha32) {
+  const int64_t j = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= np) return;
+  float acc = 0.f;
+  for (int k = lane; k < d; k += 32) {
+    const float v = j < n ? float(X[j * d + k] * hyp[d + k]) : 0.f;
+    Xs[j * d + k] = v;
+    acc = fmaf(v, v, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    bnorm[j] = acc;
+    alpha32[j] = float(alpha[j]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fast K* for d <= kFastMaxD (TF32 mode only; tolerance 1e-3):
+//   s = |a'|^2 + |b|^2 - 2 a'.b,  a' = xq/l - eps, b = x/l   ( == sum ((x - xq)/l + eps)^2 up to
+//   ~5e-6 absolute float32 cancellation error, far inside this mode's gate; the FP64 mode keeps
+//   the exact-difference form).  One FFMA per (candidate, observation, dimension).
+// 128 candidates per CTA, 8x4 register tile per thread, float4 shared loads along the feature
+// axis (row stride 4*ceil(d/4)+4 floats), candidate tile staged once, training tiles loaded into a
+// double-buffered smem tile (one barrier per tile).  grid (qc_pad/128), 256 threads, dynamic smem.
+// ------------------------------------------------------------------------------------------
+template <typename T1>
+__global__ void __launch_bounds__(256)
+k_kstar_f32_fast(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const float* __restrict__ Xs,
+                 const float* __restrict__ bnorm, int64_t n, int64_t np, const double* __restrict__ hyp,
+                 const float* __restrict__ alpha32, float* __restrict__ Ks, double* __restrict__ mu) {
+  extern __shared__ __align__(16) float ksm[];
+  const int d = h.d;
+  const int d4 = (d + 3) >> 2;
+  const int LS = 4 * d4 + 4;
+  float* x1s = ksm;                       // 128 x LS
+  float* x2s0 = x1s + 128 * LS;           // 2 x 64 x LS
+  float* als = x2s0 + 2 * 64 * LS;        // 2 x 64
+  float* bns = als + 128;                 // 2 x 64
+  float* ans = bns + 128;                 // 128
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int64_t c0 = int64_t(blockIdx.x) * 128;
+  const bool matern = h.kind == BBO_KERNEL_MATERN52;
+  const float eps = matern ? float(h.pairwise_eps) : 0.f;
+  const float s2 = float(hyp[2 * d]);
+  const int dp = 4 * d4;                  // padded feature count (zeros beyond d)
+  for (int idx = tid; idx < 128 * dp; idx += 256) {
+    const int r = idx / dp, k = idx % dp;
+    float v = 0.f;
+    if (k < d) {
+      const double x = (c0 + r < qc) ? double(Xq[(c0 + r) * d + k]) : 0.0;
+      v = float(x * hyp[d + k]) - eps;
+    }
+    x1s[r * LS + k] = v;
+  }
+  // training tile: 64 x dp floats straight into the idle buffer (visible after the tile barrier)
+  auto tload = [&](int64_t j0, int buf) {
+    float* xb = x2s0 + buf * 64 * LS;
+    for (int idx = tid; idx < 64 * dp; idx += 256) {
+      const int r = idx / dp, k = idx % dp;
+      xb[r * LS + k] = (k < d) ? Xs[(j0 + r) * d + k] : 0.f;
+    }
+    if (tid < 64) {
+      als[buf * 64 + tid] = alpha32[j0 + tid];
+      bns[buf * 64 + tid] = bnorm[j0 + tid];
+    }
+  };
+  tload(0, 0);
+  __syncthreads();
+  if (tid < 128) {
+    float acc = 0.f;
+    for (int k = 0; k < d; ++k) acc = fmaf(x1s[tid * LS + k], x1s[tid * LS + k], acc);
+    ans[tid] = acc;
+  }
+  __syncthreads();
+  float an[8], macc[8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    an[a] = ans[ty + 16 * a];
+    macc[a] = 0.f;
+  }
+  const int ntile = int(np / 64);
+  for (int t = 0; t < ntile; ++t) {
+    const int buf = t & 1;
+    const int64_t j0 = int64_t(t) * 64;
+    if (t + 1 < ntile) tload(j0 + 64, buf ^ 1);
+    float acc[8][4];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    const float* xb = x2s0 + buf * 64 * LS;
+    for (int k4 = 0; k4 < d4; ++k4) {
+      float4 av[8], bv[4];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) av[a] = *reinterpret_cast<const float4*>(&x1s[(ty + 16 * a) * LS + 4 * k4]);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) bv[b] = *reinterpret_cast<const float4*>(&xb[(tx + 16 * b) * LS + 4 * k4]);
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          acc[a][b] = fmaf(av[a].x, bv[b].x, acc[a][b]);
+          acc[a][b] = fmaf(av[a].y, bv[b].y, acc[a][b]);
+          acc[a][b] = fmaf(av[a].z, bv[b].z, acc[a][b]);
+          acc[a][b] = fmaf(av[a].w, bv[b].w, acc[a][b]);
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int64_t j = j0 + tx + 16 * b;
+      const float al = als[buf * 64 + tx + 16 * b], bn = bns[buf * 64 + tx + 16 * b];
+      const bool valid = j < n;
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        float v = 0.f;
+        if (valid) {
+          const float sq = fmaxf(fmaf(-2.f, acc[a][b], an[a] + bn), 0.f);
+          if (matern) {
+            const float r = 2.2360679775f * sqrtf(sq);
+            v = s2 * (1.f + r + r * r * (1.f / 3.f)) * __expf(-r);
+          } else {
+            v = s2 * __expf(-0.5f * sq);
+          }
+        }
+        macc[a] = fmaf(v, al, macc[a]);
+        uint32_t u;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+        Ks[(c0 + ty + 16 * a) * np + j] = __uint_as_float(u);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    float v = macc[a];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (tx == 0) mu[c0 + ty + 16 * a] = hyp[2 * d + 1] + double(v);
+  }
+}
+
+constexpr int kFastMaxD = 192;
+static size_t kstar_fast_smem(int d) {
+  const int LS = 4 * ((d + 3) / 4) + 4;
+  return sizeof(float) * (size_t(128) * LS + 2 * 64 * LS + 128 + 128 + 128);
+}
+
 // out (rows256, np): TF32-rounded copy of linv (np, np); rows >= np are zero so that every
 // 256-row TMA box of the B operand is fully in bounds.
 __global__ void k_make_tf32(int64_t valid, int64_t total, const double* __restrict__ in, float* __restrict__ out) {
@@ -370,8 +530,41 @@ int make_tf32(int64_t n, const double* linv, float* out, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-size_t score_tf32_extra_bytes(int64_t n, int64_t, int64_t qp) {
-  return size_t(qp) * size_t(padded(n)) * sizeof(float) + 256;   // float32 K* chunk
+// TF32 scratch layout inside ScoreWorkspace::tf32:
+//   Ks[2]  (qp, np) float32  double-buffered K* chunk      mu1 (qp) float64  second mu buffer
+//   Xs     (np, d)  float32  pre-scaled training inputs    alpha32 (np) float32
+struct Tf32Scratch {
+  float* Ks[2];
+  double* mu[2];
+  float* Xs;
+  float* bnorm;
+  float* alpha32;
+};
+static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+size_t score_tf32_extra_bytes(int64_t n, int64_t d, int64_t qp) {
+  const int64_t np = padded(n);
+  return 2 * align256(size_t(qp) * np * sizeof(float)) + align256(size_t(qp) * sizeof(double)) +
+         align256(size_t(np) * d * sizeof(float)) + 2 * align256(size_t(np) * sizeof(float)) + 256;
+}
+
+static Tf32Scratch carve(const ScoreWorkspace& w, int64_t d) {
+  Tf32Scratch t;
+  char* p = static_cast<char*>(w.tf32);
+  const size_t kb = align256(size_t(w.qp) * w.np * sizeof(float));
+  t.Ks[0] = reinterpret_cast<float*>(p);
+  p += kb;
+  t.Ks[1] = reinterpret_cast<float*>(p);
+  p += kb;
+  t.mu[0] = w.mu;
+  t.mu[1] = reinterpret_cast<double*>(p);
+  p += align256(size_t(w.qp) * sizeof(double));
+  t.Xs = reinterpret_cast<float*>(p);
+  p += align256(size_t(w.np) * d * sizeof(float));
+  t.bnorm = reinterpret_cast<float*>(p);
+  p += align256(size_t(w.np) * sizeof(float));
+  t.alpha32 = reinterpret_cast<float*>(p);
+  return t;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -405,27 +598,74 @@ static int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t col
   return BBO_OK;
 }
 
-int score_tf32_chunk(const bbo_gp_state& s, const ScoreWorkspace& w, const void* Xq, int xq_is_f32, int64_t qc,
-                     int64_t qc_pad, int* nsplit_out, cudaStream_t st) {
+// auxiliary stream + events of the K* / panel software pipeline (created once per device)
+struct Tf32Aux {
+  cudaStream_t sk = nullptr;
+  cudaEvent_t entry = nullptr, kdone[2] = {nullptr, nullptr}, pdone[2] = {nullptr, nullptr};
+};
+static Tf32Aux g_aux[16];
+static int get_aux(Tf32Aux** out) {
+  int dev = 0;
+  BBO_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16) return BBO_ERR_BAD_ARG;
+  Tf32Aux& a = g_aux[dev];
+  if (!a.sk) {
+    BBO_CUDA_CHECK(cudaStreamCreateWithFlags(&a.sk, cudaStreamNonBlocking));
+    BBO_CUDA_CHECK(cudaEventCreateWithFlags(&a.entry, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+      BBO_CUDA_CHECK(cudaEventCreateWithFlags(&a.kdone[i], cudaEventDisableTiming));
+      BBO_CUDA_CHECK(cudaEventCreateWithFlags(&a.pdone[i], cudaEventDisableTiming));
+    }
+  }
+  *out = &a;
+  return BBO_OK;
+}
+
+static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf32Scratch& t, int buf,
+                        const void* Xq, int xq_is_f32, int64_t qc, int64_t qc_pad, cudaStream_t st) {
+  const int64_t np = w.np;
+  prof_begin(kProfKstar, st);
+  if (s.h.d <= kFastMaxD) {
+    static int attr_d = 0;
+    const size_t ksm = kstar_fast_smem(s.h.d);
+    if (s.h.d > attr_d) {
+      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_f32_fast<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          int(kstar_fast_smem(kFastMaxD))));
+      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_f32_fast<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          int(kstar_fast_smem(kFastMaxD))));
+      attr_d = kFastMaxD;
+    }
+    if (xq_is_f32)
+      k_kstar_f32_fast<float><<<unsigned(qc_pad / 128), 256, ksm, st>>>(s.h, static_cast<const float*>(Xq), qc, t.Xs,
+                                                                     t.bnorm, s.n, np, s.hyp, t.alpha32, t.Ks[buf],
+                                                                     t.mu[buf]);
+    else
+      k_kstar_f32_fast<double><<<unsigned(qc_pad / 128), 256, ksm, st>>>(s.h, static_cast<const double*>(Xq), qc, t.Xs,
+                                                                      t.bnorm, s.n, np, s.hyp, t.alpha32, t.Ks[buf],
+                                                                      t.mu[buf]);
+  } else {
+    if (xq_is_f32)
+      k_kstar_f32<float><<<unsigned(qc_pad / 64), 256, 0, st>>>(s.h, static_cast<const float*>(Xq), qc, s.X, s.n, np,
+                                                               s.hyp, s.alpha, t.Ks[buf], t.mu[buf]);
+    else
+      k_kstar_f32<double><<<unsigned(qc_pad / 64), 256, 0, st>>>(s.h, static_cast<const double*>(Xq), qc, s.X, s.n,
+                                                                np, s.hyp, s.alpha, t.Ks[buf], t.mu[buf]);
+  }
+  BBO_LAUNCH_CHECK();
+  prof_end(kProfKstar, st);
+  return BBO_OK;
+}
+
+static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf32Scratch& t, int buf,
+                        int64_t qc_pad, int* nsplit_out, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
     BBO_CUDA_CHECK(cudaFuncSetAttribute(k_vnorm_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, tf::SMEM_BYTES));
     attr_done = true;
   }
-  float* Ks = static_cast<float*>(w.tf32);
   const int64_t np = w.np;
-  prof_begin(kProfKstar, st);
-  if (xq_is_f32)
-    k_kstar_f32<float><<<unsigned(qc_pad / 64), 256, 0, st>>>(s.h, static_cast<const float*>(Xq), qc, s.X, s.n, np,
-                                                             s.hyp, s.alpha, Ks, w.mu);
-  else
-    k_kstar_f32<double><<<unsigned(qc_pad / 64), 256, 0, st>>>(s.h, static_cast<const double*>(Xq), qc, s.X, s.n,
-                                                              np, s.hyp, s.alpha, Ks, w.mu);
-  BBO_LAUNCH_CHECK();
-  prof_end(kProfKstar, st);
-
   CUtensorMap mapA, mapB;
-  int rc = make_map(&mapA, Ks, qc_pad, np, tf::BM);
+  int rc = make_map(&mapA, t.Ks[buf], qc_pad, np, tf::BM);
   if (rc != BBO_OK) return rc;
   rc = make_map(&mapB, s.linv_tf32, tf32_rows(s.n), np, tf::BN);
   if (rc != BBO_OK) return rc;
@@ -441,6 +681,64 @@ int score_tf32_chunk(const bbo_gp_state& s, const ScoreWorkspace& w, const void*
                                                                                             w.qp, w.vpart);
   BBO_LAUNCH_CHECK();
   prof_end(kProfTf32, st);
+  return BBO_OK;
+}
+
+// Software pipeline over the chunks of one pool: K* of chunk i+1 runs on the auxiliary stream
+// (FP32 pipe) while the tcgen05 panel of chunk i runs on `st` (tensor pipe).  `consume(c0, qc, mu,
+// nsplit)` enqueues the acquisition / top-k work of a finished chunk on `st`.
+int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const void* Xq, int xq_is_f32, int64_t q,
+                        const std::function<int(int64_t, int64_t, const double*, int)>& consume, cudaStream_t st) {
+  Tf32Aux* aux = nullptr;
+  int rc = get_aux(&aux);
+  if (rc != BBO_OK) return rc;
+  // K* (FP32 pipe) and the tcgen05 panel both saturate shared-memory bandwidth, so running them
+  // concurrently gains nothing on B200 (measured: 40.7 vs 40.6 ms/step); default is one stream.
+  static const bool no_overlap = getenv("BBO_TF32_OVERLAP") == nullptr;
+  Tf32Aux serial;
+  if (no_overlap) {
+    serial = *aux;
+    serial.sk = st;
+    aux = &serial;
+  }
+  const Tf32Scratch t = carve(w, s.h.d);
+  const size_t esz = xq_is_f32 ? sizeof(float) : sizeof(double);
+  const int d = s.h.d;
+  if (d <= kFastMaxD) {
+    k_prescale<<<unsigned(ceil_div(w.np, 8)), 256, 0, st>>>(s.X, s.n, w.np, d, s.hyp, s.alpha, t.Xs, t.bnorm,
+                                                           t.alpha32);
+    BBO_LAUNCH_CHECK();
+  }
+  BBO_CUDA_CHECK(cudaEventRecord(aux->entry, st));
+  BBO_CUDA_CHECK(cudaStreamWaitEvent(aux->sk, aux->entry, 0));
+  const int64_t nchunk = ceil_div(q, w.qp);
+  auto chunk_len = [&](int64_t i) { return (q - i * w.qp < w.qp) ? q - i * w.qp : w.qp; };
+  auto chunk_ptr = [&](int64_t i) { return static_cast<const char*>(Xq) + size_t(i) * w.qp * d * esz; };
+  {
+    const int64_t qc = chunk_len(0);
+    rc = launch_kstar(s, w, t, 0, chunk_ptr(0), xq_is_f32, qc, ceil_div(qc, 128) * 128, aux->sk);
+    if (rc != BBO_OK) return rc;
+    BBO_CUDA_CHECK(cudaEventRecord(aux->kdone[0], aux->sk));
+  }
+  for (int64_t i = 0; i < nchunk; ++i) {
+    const int buf = int(i & 1);
+    if (i + 1 < nchunk) {
+      const int nb = buf ^ 1;
+      if (i >= 1) BBO_CUDA_CHECK(cudaStreamWaitEvent(aux->sk, aux->pdone[nb], 0));   // chunk i-1 released buffer nb
+      const int64_t qn = chunk_len(i + 1);
+      rc = launch_kstar(s, w, t, nb, chunk_ptr(i + 1), xq_is_f32, qn, ceil_div(qn, 128) * 128, aux->sk);
+      if (rc != BBO_OK) return rc;
+      BBO_CUDA_CHECK(cudaEventRecord(aux->kdone[nb], aux->sk));
+    }
+    const int64_t qc = chunk_len(i);
+    BBO_CUDA_CHECK(cudaStreamWaitEvent(st, aux->kdone[buf], 0));
+    int nsplit = 1;
+    rc = launch_panel(s, w, t, buf, ceil_div(qc, 128) * 128, &nsplit, st);
+    if (rc != BBO_OK) return rc;
+    rc = consume(i * w.qp, qc, t.mu[buf], nsplit);
+    if (rc != BBO_OK) return rc;
+    BBO_CUDA_CHECK(cudaEventRecord(aux->pdone[buf], st));
+  }
   return BBO_OK;
 }
 

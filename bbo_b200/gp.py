@@ -355,7 +355,8 @@ class CudaGP(Surrogate):
                 if Xq.is_cuda:
                     raise ValueError("host_pool=True expects a CPU tensor")
                 xq = Xq.contiguous()
-                staging = self._workspace("staging%d" % int(is_f32), 2 * qc * self.d * (4 if is_f32 else 8))
+                staging = self._workspace("staging%d" % int(is_f32),
+                                          2 * _lib.HOST_STAGE_CHUNKS * qc * self.d * (4 if is_f32 else 8))
                 hs = torch.empty(k, dtype=_F64)
                 hi = torch.empty(k, dtype=torch.int64)
                 _lib.check(self._lib.bbo_gp_score_pool_host(

@@ -68,6 +68,7 @@ typedef enum bbo_precision { BBO_PREC_FP64 = 0, BBO_PREC_TF32 = 1 } bbo_precisio
 
 #define BBO_ROW_ALIGN 128   /* n is padded to a multiple of this in all n x n buffers */
 #define BBO_TOPK_MAX 128
+#define BBO_HOST_STAGE_CHUNKS 4   /* bbo_gp_score_pool_host copies this many chunks per H2D transfer */
 
 int bbo_version(void);
 /* text of the last CUDA error seen by this thread ("" if none) */
@@ -221,8 +222,8 @@ int bbo_gp_score_pool(const bbo_gp_state* st, const bbo_acq* acq, int32_t precis
 
 /* Same with the candidate pool in HOST memory (pinned for full overlap).  The pool is
  * streamed to the device in chunks of q_chunk rows on an internal copy stream, double
- * buffered against the scoring kernels; staging_dev must hold 2*q_chunk*d elements of the
- * candidate dtype.  topk_*_host receive the result; the call synchronises `stream`.       */
+ * buffered against the scoring kernels; staging_dev must hold
+ * 2*BBO_HOST_STAGE_CHUNKS*q_chunk*d elements of the candidate dtype (q_chunk rounded up to 128).  topk_*_host receive the result; the call synchronises `stream`.       */
 int bbo_gp_score_pool_host(const bbo_gp_state* st, const bbo_acq* acq, int32_t precision,
                            const void* Xq_host, int32_t xq_is_f32, int64_t q, int64_t index_offset,
                            int32_t k, double* topk_score_host, int64_t* topk_index_host,

@@ -16,7 +16,8 @@ TOL = 1e-3
     (100, 20, 700, O.RBF),          # np = 128: a single, zero-padded 256-row block
     (300, 20, 5000, O.MATERN52),    # np = 384: partial last block
     (1024, 20, 20000, O.RBF),       # config-2 shape, > 148 tiles (chunk of 148 x 128)
-    (515, 33, 3000, O.MATERN52),    # feature chunking (d > 32)
+    (515, 33, 3000, O.MATERN52),    # d not a multiple of 4
+    (260, 100, 2000, O.RBF),        # config-5 dimensionality
 ])
 def test_tf32_posterior_and_selection(n, d, q, kind, cuda_device):
     import bbo_b200 as B
