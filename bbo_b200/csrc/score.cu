@@ -349,11 +349,12 @@ int topk_merge(const double* score, const int64_t* index, int64_t m, int k, doub
 // ==========================================================================================
 static int64_t round_chunk(int64_t q_chunk) { return ceil_div(q_chunk < 128 ? 128 : q_chunk, 128) * 128; }
 
-static int pick_nsplit(int64_t qc_pad, int64_t np) {
-  int64_t want = ceil_div(2 * 148, qc_pad / 128);
-  int64_t cap = np / 64;
-  if (want > cap) want = cap;
-  if (want > kMaxSplit) want = kMaxSplit;
+// Number of row-tile splits of the variance panel.  It must depend on n ONLY: the partial sums of
+// a candidate are then associated identically for every chunking / sharding of the pool, which is
+// what makes the multi-GPU selection bit-identical to the single-GPU one.
+static int pick_nsplit(int64_t /*qc_pad*/, int64_t np) {
+  int64_t want = np / 64;
+  if (want > 8) want = 8;
   if (want < 1) want = 1;
   return int(want);
 }

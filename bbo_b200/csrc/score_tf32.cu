@@ -671,10 +671,10 @@ static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
   if (rc != BBO_OK) return rc;
   const int64_t tiles = qc_pad / tf::BM;
   const int64_t nblk = ceil_div(np, tf::BN);
-  int64_t nsplit = ceil_div(148, tiles);          // fill the 148 SMs when the chunk is small
-  if (nsplit > nblk) nsplit = nblk;
-  if (nsplit > kMaxSplit) nsplit = kMaxSplit;
-  if (nsplit < 1) nsplit = 1;
+  // one CTA walks all 256-row blocks of its candidate tile: the split count never depends on the
+  // chunk size, so results are bit-identical for every chunking / sharding of the pool
+  const int64_t nsplit = 1;
+  (void)nblk;
   *nsplit_out = int(nsplit);
   prof_begin(kProfTf32, st);
   k_vnorm_tf32<<<dim3(unsigned(tiles), unsigned(nsplit)), tf::THREADS, tf::SMEM_BYTES, st>>>(mapA, mapB, int(np),
