@@ -1,0 +1,56 @@
+"""GPU parity of the batched small-problem path (BASELINE config 4 shape, scaled down for the oracle)."""
+import numpy as np
+import pytest
+import torch
+
+from _golden import O
+from _gpu_helpers import np_, synth_problem
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(B, n, d, kind, seed):
+    ps, Xs, ys = [], [], []
+    for b in range(B):
+        p, X, y = synth_problem(seed + b, n, d, kind=kind, noise=1e-4)
+        ps.append(p), Xs.append(X), ys.append(y)
+    theta = np.stack([np.concatenate([[p.constant], np.atleast_1d(p.raw_lengthscale), [p.raw_variance]]) for p in ps])
+    return ps, np.stack(Xs), np.stack(ys), theta
+
+
+@pytest.mark.parametrize("B,n,d,kind", [(5, 70, 4, O.MATERN52), (3, 256, 10, O.RBF)])
+def test_batched_value_grad_train_and_scoring(B, n, d, kind, cuda_device):
+    import bbo_b200 as B200
+    from bbo_b200.batch import CudaGPBatch
+    ps, X, y, theta = _batch(B, n, d, kind, 300)
+    impl = "rbf_vmap" if kind == O.RBF else "matern52_vmap"
+    gb = CudaGPBatch(torch.as_tensor(X), torch.as_tensor(y)[..., None], impl, theta=torch.as_tensor(theta),
+                     noise_variance=1e-4, epochs=6, lr=0.01)
+    vals, grads = gb.value_and_grad()
+    for b in range(B):
+        oval, og_ls, og_var, og_c = O.objective_value_and_grad(ps[b], X[b], y[b])
+        assert abs(float(vals[b]) - oval) <= 1e-7 * abs(oval)
+        ls = O.softplus(ps[b].raw_lengthscale).numpy()
+        # oracle gradients are w.r.t. raw parameters: undo the softplus chain rule
+        g_l = og_ls / O.sigmoid(ps[b].raw_lengthscale).numpy()
+        np.testing.assert_allclose(np_(grads[b, :d]), g_l, rtol=0, atol=1e-6 * np.abs(g_l).max())
+        assert abs(float(grads[b, d]) - og_var / float(O.sigmoid(ps[b].raw_variance))) <= 1e-6 * abs(og_var) + 1e-9
+        assert abs(float(grads[b, d + 1]) - og_c) <= 1e-6 * abs(og_c) + 1e-9
+        assert ls.shape == (d,)
+    # batched scoring before training == per-problem oracle
+    q, k = 600, 4
+    Xq = np.random.default_rng(1).random((B, q, d))
+    s, i = gb.score_pools(torch.as_tensor(Xq), lambda b: B200.EI(float(y[b].max())), k)
+    for b in range(B):
+        oi, os_, *_ = O.score_pool(ps[b], X[b], y[b], Xq[b], "ei", float(y[b].max()), k=k)
+        np.testing.assert_array_equal(np_(i[b]), oi)
+        np.testing.assert_allclose(np_(s[b]), os_, rtol=1e-6, atol=1e-12)
+    # batched Adam == per-problem oracle Adam (gp.py:54-63, sign=+1 as in the reference)
+    gb.train()
+    for b in range(B):
+        final, ovals = O.adam_train(ps[b], X[b], y[b], lr=0.01, epochs=6)
+        got = np_(gb.theta[b])
+        want = np.concatenate([[final.constant], np.atleast_1d(final.raw_lengthscale), [final.raw_variance]])
+        np.testing.assert_allclose(got, want, rtol=1e-7, atol=1e-9)
+        np.testing.assert_allclose(np_(gb.last_values[:, b]), ovals, rtol=1e-7)
+    assert int(gb.info.abs().sum()) == 0

@@ -48,5 +48,24 @@ def main():
              "score_fp64_ms": t_sc, "score_fp64_cand_per_s": q / t_sc * 1e3, "score_fp64_tflops": flops / t_sc / 1e9}
         print(json.dumps(r), flush=True)
 
+def batched():
+    from bbo_b200.batch import CudaGPBatch
+    B_, n, d = 256, 256, 10
+    rng = np.random.default_rng(1)
+    X = torch.as_tensor(rng.random((B_, n, d))); y = torch.sin(X.sum(-1, keepdim=True) * 3)
+    y = (y - y.mean(1, keepdim=True)) / y.std(1, keepdim=True)
+    th = torch.zeros(B_, 1 + d + 1, dtype=torch.float64); th[:, 1:] = 0.3
+    gb = CudaGPBatch(X, y, "matern52_vmap", theta=th, noise_variance=1e-4, epochs=10)
+    t = ev_time(lambda: gb.value_and_grad(), reps=3)
+    t0 = time.time(); gb.train(); torch.cuda.synchronize(); tt = (time.time() - t0) / 10
+    Xq = torch.rand(B_, 4096, d, dtype=torch.float64, device="cuda")
+    gb.score_pools(Xq, lambda b: B.EI(1.0), 4); torch.cuda.synchronize()
+    t0 = time.time(); gb.score_pools(Xq, lambda b: B.EI(1.0), 4); torch.cuda.synchronize(); ts = time.time() - t0
+    print(json.dumps({"config4": "256 x (n=256, d=10)", "value_grad_ms_all": t, "train_ms_per_epoch_all": tt * 1e3,
+                      "fits_per_s": B_ / (t * 1e-3), "score_256x4096_s": ts, "cand_per_s": B_ * 4096 / ts}), flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "batched":
+        batched(); sys.exit(0)
     main()
