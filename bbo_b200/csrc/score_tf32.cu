@@ -381,7 +381,7 @@ k_prescale(const double* __restrict__ X, int64_t n, int64_t np, int d, const dou
 //   ~5e-6 absolute float32 cancellation error, far inside this mode's gate; the FP64 mode keeps
 //   the exact-difference form).  One FFMA per (candidate, observation, dimension).
 // 128 candidates per CTA, 8x4 register tile per thread, float4 shared loads along the feature
-// axis (row stride 4*ceil(d/4)+4 floats), candidate tile staged once, training tiles loaded into a
+// axis (row stride = smallest 4*odd >= d+4 floats), candidate tile staged once, training tiles loaded into a
 // double-buffered smem tile (one barrier per tile).  grid (qc_pad/128), 256 threads, dynamic smem.
 // ------------------------------------------------------------------------------------------
 template <typename T1>
@@ -392,7 +392,7 @@ k_kstar_f32_fast(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const fl
   extern __shared__ __align__(16) float ksm[];
   const int d = h.d;
   const int d4 = (d + 3) >> 2;
-  const int LS = 4 * d4 + 4;
+  const int LS = 4 * ((d4 + 1) | 1);      // row stride: LS/4 odd -> float4 reads conflict free per quarter warp
   float* x1s = ksm;                       // 128 x LS
   float* x2s0 = x1s + 128 * LS;           // 2 x 64 x LS
   float* als = x2s0 + 2 * 64 * LS;        // 2 x 64
@@ -502,7 +502,7 @@ k_kstar_f32_fast(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const fl
 
 constexpr int kFastMaxD = 192;
 static size_t kstar_fast_smem(int d) {
-  const int LS = 4 * ((d + 3) / 4) + 4;
+  const int LS = 4 * ((((d + 3) / 4) + 1) | 1);
   return sizeof(float) * (size_t(128) * LS + 2 * 64 * LS + 128 + 128 + 128);
 }
 
