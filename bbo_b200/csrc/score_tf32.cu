@@ -500,6 +500,189 @@ k_kstar_f32_fast(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const fl
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// K* on the tensor cores (TF32 mode, d <= kMmaMaxD): the scaled dot products a'.b are computed with
+// error-compensated 3xTF32 (a_hi b_hi + a_hi b_lo + a_lo b_hi, relative error ~2^-21) on
+// mma.sync.m16n8k8.tf32 (SASS HMMA.1688.F32.TF32), which removes the 20 FFMA per (candidate,
+// observation) of the CUDA-core version and leaves the exp epilogue and the store.
+//   s = |a'|^2 + |b|^2 - 2 a'.b ;  RBF: k = s2 exp(-s/2) = 2^(log2e * a'.b + A'_row + B'_col)
+// 128 candidates per CTA (8 warps x 16 rows), A fragments (hi/lo) live in registers for the whole
+// kernel, 64-observation tiles of the pre-split training set are cp.async double buffered.
+// grid (qc_pad/128), 256 threads, dynamic smem.
+// ------------------------------------------------------------------------------------------
+constexpr int kMmaMaxD = 64;
+
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// pre-split training set: Xhi/Xlo (np, dk) TF32 bit patterns of X/l, dk = 8*ceil(d/8) (zero padded)
+__global__ void __launch_bounds__(256)
+k_prescale_split(const double* __restrict__ X, int64_t n, int64_t np, int d, int dk, const double* __restrict__ hyp,
+                 const double* __restrict__ alpha, uint32_t* __restrict__ Xhi, uint32_t* __restrict__ Xlo,
+                 float* __restrict__ bnorm, float* __restrict__ alpha32) {
+  const int64_t j = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= np) return;
+  float acc = 0.f;
+  for (int k = lane; k < dk; k += 32) {
+    const float v = (j < n && k < d) ? float(X[j * d + k] * hyp[d + k]) : 0.f;
+    uint32_t hi, lo;
+    split_tf32(v, hi, lo);
+    Xhi[j * dk + k] = hi;
+    Xlo[j * dk + k] = lo;
+    acc = fmaf(v, v, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    bnorm[j] = acc;
+    alpha32[j] = float(alpha[j]);
+  }
+}
+
+template <typename T1, int KS>   // KS = dk / 8 k-steps
+__global__ void __launch_bounds__(256)
+k_kstar_mma(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const uint32_t* __restrict__ Xhi,
+            const uint32_t* __restrict__ Xlo, const float* __restrict__ bnorm, int64_t n, int64_t np,
+            const double* __restrict__ hyp, const float* __restrict__ alpha32, float* __restrict__ Ks,
+            double* __restrict__ mu) {
+  constexpr int DK = KS * 8;
+  constexpr int LS = 4 * ((DK / 4 + 1) | 1);   // LS/4 odd: fragment loads conflict free
+  extern __shared__ __align__(16) uint32_t msm[];
+  uint32_t* bhi = msm;                   // 2 x 64 x LS
+  uint32_t* blo = bhi + 2 * 64 * LS;     // 2 x 64 x LS
+  float* bns = reinterpret_cast<float*>(blo + 2 * 64 * LS);   // 2 x 64
+  float* als = bns + 128;                                     // 2 x 64
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int d = h.d;
+  const bool matern = h.kind == BBO_KERNEL_MATERN52;
+  const float eps = matern ? float(h.pairwise_eps) : 0.f;
+  const float s2 = float(hyp[2 * d]);
+  const float kLog2e = 1.4426950408889634f;
+  const float l2s2 = __log2f(s2);
+  const int64_t row0 = int64_t(blockIdx.x) * 128 + warp * 16;   // this warp's 16 candidates
+
+  // A fragments: a0 (g, t), a1 (g+8, t), a2 (g, t+4), a3 (g+8, t+4) per k-step; a' = xq/l - eps
+  uint32_t ahi[KS][4], alo[KS][4];
+  float an0 = 0.f, an1 = 0.f;   // |a'|^2 of rows g and g+8 (partial over this lane's k)
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      const int64_t r = row0 + g + ((f & 1) ? 8 : 0);
+      const int k = ks * 8 + t + ((f & 2) ? 4 : 0);
+      float v = 0.f;
+      if (k < d) {
+        const double x = (r < qc) ? double(Xq[r * d + k]) : 0.0;
+        v = float(x * hyp[d + k]) - eps;
+      }
+      split_tf32(v, ahi[ks][f], alo[ks][f]);
+      if (f & 1) an1 = fmaf(v, v, an1);
+      else an0 = fmaf(v, v, an0);
+    }
+  }
+  an0 += __shfl_xor_sync(0xffffffffu, an0, 1);
+  an0 += __shfl_xor_sync(0xffffffffu, an0, 2);
+  an1 += __shfl_xor_sync(0xffffffffu, an1, 1);
+  an1 += __shfl_xor_sync(0xffffffffu, an1, 2);
+  const float Ap0 = fmaf(-0.5f * kLog2e, an0, l2s2), Ap1 = fmaf(-0.5f * kLog2e, an1, l2s2);
+
+  auto tload = [&](int64_t j0, int buf) {
+    // 64 rows x DK words, 16-byte chunks, both arrays
+    constexpr int CH = DK / 4;
+    for (int c = tid; c < 64 * CH * 2; c += 256) {
+      const int arr = c / (64 * CH), rem = c % (64 * CH), r = rem / CH, ch = rem % CH;
+      const uint32_t* src = (arr ? Xlo : Xhi) + (j0 + r) * DK + ch * 4;
+      uint32_t* dst = (arr ? blo : bhi) + (buf * 64 + r) * LS + ch * 4;
+      const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(dst));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src));
+    }
+    if (tid < 64) {
+      bns[buf * 64 + tid] = bnorm[j0 + tid];
+      als[buf * 64 + tid] = alpha32[j0 + tid];
+    }
+    asm volatile("cp.async.commit_group;");
+  };
+  tload(0, 0);
+  float m0 = 0.f, m1 = 0.f;   // mu partials of rows g, g+8
+  const int ntile = int(np / 64);
+  float* out0 = Ks + (row0 + g) * np;
+  float* out1 = Ks + (row0 + g + 8) * np;
+  for (int tl = 0; tl < ntile; ++tl) {
+    const int buf = tl & 1;
+    const int64_t j0 = int64_t(tl) * 64;
+    asm volatile("cp.async.wait_group 0;");
+    __syncthreads();                                   // tile tl visible; everyone is done with tile tl-1
+    if (tl + 1 < ntile) tload(j0 + 64, buf ^ 1);
+    const uint32_t* ph = bhi + buf * 64 * LS;
+    const uint32_t* pl = blo + buf * 64 * LS;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const int o = (nt * 8 + g) * LS + ks * 8 + t;   // b0 (k=t, n=g), b1 (k=t+4, n=g)
+        const uint32_t h0 = ph[o], h1 = ph[o + 4], l0 = pl[o], l1 = pl[o + 4];
+        mma_tf32_16x8x8(c, alo[ks], h0, h1);
+        mma_tf32_16x8x8(c, ahi[ks], l0, l1);
+        mma_tf32_16x8x8(c, ahi[ks], h0, h1);
+      }
+      const int cl = nt * 8 + 2 * t;
+      const int64_t j = j0 + cl;
+      const float bn0 = bns[buf * 64 + cl], bn1 = bns[buf * 64 + cl + 1];
+      const float al0 = als[buf * 64 + cl], al1 = als[buf * 64 + cl + 1];
+      float v[4];
+      if (!matern) {
+        const float B0 = -0.5f * kLog2e * bn0, B1 = -0.5f * kLog2e * bn1;
+        v[0] = exp2f(fminf(fmaf(c[0], kLog2e, Ap0 + B0), l2s2));
+        v[1] = exp2f(fminf(fmaf(c[1], kLog2e, Ap0 + B1), l2s2));
+        v[2] = exp2f(fminf(fmaf(c[2], kLog2e, Ap1 + B0), l2s2));
+        v[3] = exp2f(fminf(fmaf(c[3], kLog2e, Ap1 + B1), l2s2));
+      } else {
+        const float sq[4] = {fmaf(-2.f, c[0], an0 + bn0), fmaf(-2.f, c[1], an0 + bn1),
+                             fmaf(-2.f, c[2], an1 + bn0), fmaf(-2.f, c[3], an1 + bn1)};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float r = 2.2360679775f * sqrtf(fmaxf(sq[e], 0.f));
+          v[e] = s2 * (1.f + r + r * r * (1.f / 3.f)) * __expf(-r);
+        }
+      }
+      if (j >= n) v[0] = v[2] = 0.f;
+      if (j + 1 >= n) v[1] = v[3] = 0.f;
+      m0 = fmaf(v[0], al0, fmaf(v[1], al1, m0));
+      m1 = fmaf(v[2], al0, fmaf(v[3], al1, m1));
+      uint32_t u[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u[e]) : "f"(v[e]));
+      *reinterpret_cast<uint2*>(out0 + j) = make_uint2(u[0], u[1]);
+      *reinterpret_cast<uint2*>(out1 + j) = make_uint2(u[2], u[3]);
+    }
+  }
+  m0 += __shfl_xor_sync(0xffffffffu, m0, 1);
+  m0 += __shfl_xor_sync(0xffffffffu, m0, 2);
+  m1 += __shfl_xor_sync(0xffffffffu, m1, 1);
+  m1 += __shfl_xor_sync(0xffffffffu, m1, 2);
+  if (t == 0) {
+    mu[row0 + g] = hyp[2 * d + 1] + double(m0);
+    mu[row0 + g + 8] = hyp[2 * d + 1] + double(m1);
+  }
+}
+
+template <int KS>
+static size_t kstar_mma_smem() {
+  constexpr int DK = KS * 8, LS = 4 * ((DK / 4 + 1) | 1);
+  return sizeof(uint32_t) * (size_t(4) * 64 * LS) + sizeof(float) * 256;
+}
+
 constexpr int kFastMaxD = 192;
 static size_t kstar_fast_smem(int d) {
   const int LS = 4 * ((((d + 3) / 4) + 1) | 1);
@@ -539,13 +722,16 @@ struct Tf32Scratch {
   float* Xs;
   float* bnorm;
   float* alpha32;
+  uint32_t* Xhi;
+  uint32_t* Xlo;
 };
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 size_t score_tf32_extra_bytes(int64_t n, int64_t d, int64_t qp) {
   const int64_t np = padded(n);
   return 2 * align256(size_t(qp) * np * sizeof(float)) + align256(size_t(qp) * sizeof(double)) +
-         align256(size_t(np) * d * sizeof(float)) + 2 * align256(size_t(np) * sizeof(float)) + 256;
+         align256(size_t(np) * d * sizeof(float)) + 2 * align256(size_t(np) * sizeof(float)) +
+         2 * align256(size_t(np) * (d + 8) * sizeof(uint32_t)) + 256;
 }
 
 static Tf32Scratch carve(const ScoreWorkspace& w, int64_t d) {
@@ -564,6 +750,10 @@ static Tf32Scratch carve(const ScoreWorkspace& w, int64_t d) {
   t.bnorm = reinterpret_cast<float*>(p);
   p += align256(size_t(w.np) * sizeof(float));
   t.alpha32 = reinterpret_cast<float*>(p);
+  p += align256(size_t(w.np) * sizeof(float));
+  t.Xhi = reinterpret_cast<uint32_t*>(p);
+  p += align256(size_t(w.np) * (d + 8) * sizeof(uint32_t));
+  t.Xlo = reinterpret_cast<uint32_t*>(p);
   return t;
 }
 
@@ -625,7 +815,42 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
                         const void* Xq, int xq_is_f32, int64_t qc, int64_t qc_pad, cudaStream_t st) {
   const int64_t np = w.np;
   prof_begin(kProfKstar, st);
-  if (s.h.d <= kFastMaxD) {
+  static const bool use_mma = getenv("BBO_KSTAR_NO_MMA") == nullptr;
+  if (use_mma && s.h.d <= kMmaMaxD) {
+    const int ks = (s.h.d + 7) / 8;
+    const unsigned grid = unsigned(qc_pad / 128);
+#define BBO_KSTAR_MMA(KS_)                                                                                     \
+  case KS_: {                                                                                                  \
+    const size_t sm = kstar_mma_smem<KS_>();                                                                   \
+    static bool attr_set = false;                                                                              \
+    if (!attr_set && sm > 48 * 1024) {                                                                         \
+      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_mma<float, KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          int(sm)));                                                           \
+      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_mma<double, KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          int(sm)));                                                           \
+      attr_set = true;                                                                                         \
+    }                                                                                                          \
+    if (xq_is_f32)                                                                                             \
+      k_kstar_mma<float, KS_><<<grid, 256, sm, st>>>(s.h, static_cast<const float*>(Xq), qc, t.Xhi, t.Xlo,      \
+                                                     t.bnorm, s.n, np, s.hyp, t.alpha32, t.Ks[buf], t.mu[buf]);  \
+    else                                                                                                       \
+      k_kstar_mma<double, KS_><<<grid, 256, sm, st>>>(s.h, static_cast<const double*>(Xq), qc, t.Xhi, t.Xlo,    \
+                                                      t.bnorm, s.n, np, s.hyp, t.alpha32, t.Ks[buf], t.mu[buf]); \
+  } break;
+    switch (ks) {
+      BBO_KSTAR_MMA(1)
+      BBO_KSTAR_MMA(2)
+      BBO_KSTAR_MMA(3)
+      BBO_KSTAR_MMA(4)
+      BBO_KSTAR_MMA(5)
+      BBO_KSTAR_MMA(6)
+      BBO_KSTAR_MMA(7)
+      BBO_KSTAR_MMA(8)
+      default:
+        return BBO_ERR_BAD_ARG;
+    }
+#undef BBO_KSTAR_MMA
+  } else if (s.h.d <= kFastMaxD) {
     static int attr_d = 0;
     const size_t ksm = kstar_fast_smem(s.h.d);
     if (s.h.d > attr_d) {
@@ -704,7 +929,13 @@ int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const vo
   const Tf32Scratch t = carve(w, s.h.d);
   const size_t esz = xq_is_f32 ? sizeof(float) : sizeof(double);
   const int d = s.h.d;
-  if (d <= kFastMaxD) {
+  static const bool use_mma = getenv("BBO_KSTAR_NO_MMA") == nullptr;
+  if (use_mma && d <= kMmaMaxD) {
+    const int dk = 8 * ((d + 7) / 8);
+    k_prescale_split<<<unsigned(ceil_div(w.np, 8)), 256, 0, st>>>(s.X, s.n, w.np, d, dk, s.hyp, s.alpha, t.Xhi, t.Xlo,
+                                                                 t.bnorm, t.alpha32);
+    BBO_LAUNCH_CHECK();
+  } else if (d <= kFastMaxD) {
     k_prescale<<<unsigned(ceil_div(w.np, 8)), 256, 0, st>>>(s.X, s.n, w.np, d, s.hyp, s.alpha, t.Xs, t.bnorm,
                                                            t.alpha32);
     BBO_LAUNCH_CHECK();
