@@ -224,7 +224,10 @@ k_vnorm_tf32(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     // ===================== epilogue (warps 2..5) =====================
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;                // candidate row within the tile
-    double total = 0.0;
+    // Four fixed accumulation slots (row block index mod 4): the association of a candidate's partial
+    // sums is the same whether 1, 2 or 4 CTAs share the tile, so the host may pick the split by
+    // occupancy without changing a single bit of the result.
+    double tot0 = 0.0, tot1 = 0.0, tot2 = 0.0, tot3 = 0.0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int nb = blockIdx.y; nb < nblk; nb += gridDim.y) {
@@ -246,7 +249,11 @@ k_vnorm_tf32(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         }
         part += (s0 + s1) + (s2 + s3);
       }
-      total += double(part);
+      const int slot = nb & 3;
+      if (slot == 0) tot0 += double(part);
+      else if (slot == 1) tot1 += double(part);
+      else if (slot == 2) tot2 += double(part);
+      else tot3 += double(part);
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) {
@@ -254,7 +261,11 @@ k_vnorm_tf32(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         acc_phase ^= 1;
       }
     }
-    vpart[int64_t(blockIdx.y) * qc_pad + c0 + row] = total;
+    // this CTA owns the slots g with g % gridDim.y == blockIdx.y (gridDim.y in {1,2,4})
+    const double tots[4] = {tot0, tot1, tot2, tot3};
+#pragma unroll
+    for (int g4 = 0; g4 < 4; ++g4)
+      if (g4 % int(gridDim.y) == int(blockIdx.y)) vpart[int64_t(g4) * qc_pad + c0 + row] = tots[g4];
   }
 
   tc_fence_before();
@@ -510,7 +521,7 @@ k_kstar_f32_fast(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const fl
 // kernel, 64-observation tiles of the pre-split training set are cp.async double buffered.
 // grid (qc_pad/128), 256 threads, dynamic smem.
 // ------------------------------------------------------------------------------------------
-constexpr int kMmaMaxD = 64;
+constexpr int kMmaMaxD = 128;
 
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
@@ -846,6 +857,14 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
       BBO_KSTAR_MMA(6)
       BBO_KSTAR_MMA(7)
       BBO_KSTAR_MMA(8)
+      BBO_KSTAR_MMA(9)
+      BBO_KSTAR_MMA(10)
+      BBO_KSTAR_MMA(11)
+      BBO_KSTAR_MMA(12)
+      BBO_KSTAR_MMA(13)
+      BBO_KSTAR_MMA(14)
+      BBO_KSTAR_MMA(15)
+      BBO_KSTAR_MMA(16)
       default:
         return BBO_ERR_BAD_ARG;
     }
@@ -896,11 +915,12 @@ static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
   if (rc != BBO_OK) return rc;
   const int64_t tiles = qc_pad / tf::BM;
   const int64_t nblk = ceil_div(np, tf::BN);
-  // one CTA walks all 256-row blocks of its candidate tile: the split count never depends on the
-  // chunk size, so results are bit-identical for every chunking / sharding of the pool
-  const int64_t nsplit = 1;
-  (void)nblk;
-  *nsplit_out = int(nsplit);
+  // the 256-row blocks of a candidate tile are dealt round-robin to 1, 2 or 4 CTAs, chosen by
+  // occupancy; partial sums always go to four fixed slots (block index mod 4), so the result is
+  // bit-identical for every split, chunking and sharding of the pool.
+  int64_t nsplit = tiles >= 148 ? 1 : (2 * tiles >= 148 ? 2 : 4);
+  if (nblk < 2) nsplit = 1;
+  *nsplit_out = 4;   // k_acq always sums the four slots
   prof_begin(kProfTf32, st);
   k_vnorm_tf32<<<dim3(unsigned(tiles), unsigned(nsplit)), tf::THREADS, tf::SMEM_BYTES, st>>>(mapA, mapB, int(np),
                                                                                             w.qp, w.vpart);
