@@ -79,10 +79,23 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask)
                : "memory");
 }
 __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -302,10 +315,17 @@ __device__ __forceinline__ uint64_t make_desc64(uint32_t saddr) {
 }
 }  // namespace tfp
 
+// CL = 2: clusters of two CTAs (adjacent candidate tiles, same row blocks).  Each CTA loads HALF of
+// every L^-1 tile and TMA-multicasts it to both, so the B operand crosses L2->SM once per cluster;
+// a stage is released to the producers only when BOTH tensor cores have consumed it
+// (tcgen05.commit multicast onto both CTAs' empty barriers, count 2).
+template <int CL>
 __global__ void __launch_bounds__(tf::THREADS, 1)
 k_vnorm_tf32_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int np,
                   int64_t qc_pad, double* __restrict__ vpart) {
   using namespace tf;
+  uint32_t cta_rank = 0;
+  if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[tfp::STAGES], empty_bar[tfp::STAGES], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_sh;
@@ -319,7 +339,7 @@ k_vnorm_tf32_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   if (threadIdx.x == 0) {
     for (int s = 0; s < tfp::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
@@ -335,6 +355,10 @@ k_vnorm_tf32_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) {   // peers' barriers must be initialised before any remote arrive / multicast lands
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_sh;
 
@@ -353,8 +377,20 @@ k_vnorm_tf32_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           uint8_t* sa = sgen + stage * tfp::STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], tfp::A_BYTES + (act0 ? tfp::B_BYTES : 0) + (has1 ? tfp::B_BYTES : 0));
           tma_load_2d(sa, &mapA, &full_bar[stage], k, c0);
-          if (act0) tma_load_2d(sa + tfp::A_BYTES, &mapB, &full_bar[stage], k, b0 * tfp::BN);
-          if (has1) tma_load_2d(sa + tfp::A_BYTES + tfp::B_BYTES, &mapB, &full_bar[stage], k, b1 * tfp::BN);
+          if (CL == 1) {
+            if (act0) tma_load_2d(sa + tfp::A_BYTES, &mapB, &full_bar[stage], k, b0 * tfp::BN);
+            if (has1) tma_load_2d(sa + tfp::A_BYTES + tfp::B_BYTES, &mapB, &full_bar[stage], k, b1 * tfp::BN);
+          } else {   // my half of each L^-1 tile, multicast to both CTAs of the cluster
+            constexpr int HR = tfp::BN / CL;                 // rows per slice
+            constexpr int HB = tfp::B_BYTES / CL;            // bytes per slice
+            const uint16_t mask = uint16_t((1u << CL) - 1u);
+            if (act0)
+              tma_load_2d_mc(sa + tfp::A_BYTES + cta_rank * HB, &mapB, &full_bar[stage], k,
+                             b0 * tfp::BN + int(cta_rank) * HR, mask);
+            if (has1)
+              tma_load_2d_mc(sa + tfp::A_BYTES + tfp::B_BYTES + cta_rank * HB, &mapB, &full_bar[stage], k,
+                             b1 * tfp::BN + int(cta_rank) * HR, mask);
+          }
           if (++stage == tfp::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -395,7 +431,8 @@ k_vnorm_tf32_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constan
               tc_mma_tf32(tmem_base + uint32_t(tfp::BN), adesc + uint64_t(kk * 2), bdesc + uint64_t(kk * 2), idesc,
                           (k | kk) != 0 ? 1u : 0u);
           }
-          tc_commit(&empty_bar[stage]);
+          if (CL == 1) tc_commit(&empty_bar[stage]);
+          else tc_commit_mc(&empty_bar[stage], uint16_t((1u << CL) - 1u));   // frees the stage in BOTH CTAs
           if (k + tfp::BK == kend0) tc_commit(&tfull_bar[0]);   // block b0 complete: drain it while b1 finishes
           if (++stage == tfp::STAGES) {
             stage = 0;
@@ -451,6 +488,10 @@ k_vnorm_tf32_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) {   // no CTA may exit while its peer can still multicast into it / arrive on its barriers
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -1090,17 +1131,21 @@ static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
     attr_done = true;
   }
   const int64_t np = w.np;
-  static const bool pair = getenv("BBO_TF32_SINGLE") == nullptr;   // paired row blocks by default
+  static const bool pair = getenv("BBO_TF32_SINGLE") == nullptr;    // paired row blocks by default
+  static const bool clus = getenv("BBO_TF32_NO_CLUSTER") == nullptr; // 2-CTA clusters with TMA multicast
   static bool attr2 = false;
   if (pair && !attr2) {
-    BBO_CUDA_CHECK(cudaFuncSetAttribute(k_vnorm_tf32_pair, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    BBO_CUDA_CHECK(cudaFuncSetAttribute(k_vnorm_tf32_pair<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        tfp::SMEM_BYTES));
+    BBO_CUDA_CHECK(cudaFuncSetAttribute(k_vnorm_tf32_pair<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         tfp::SMEM_BYTES));
     attr2 = true;
   }
+  const bool use_cluster = pair && clus && (qc_pad / tf::BM) % 2 == 0;
   CUtensorMap mapA, mapB;
   int rc = make_map(&mapA, t.Ks[buf], qc_pad, np, tf::BM, pair ? tfp::BK : tf::BK);
   if (rc != BBO_OK) return rc;
-  rc = make_map(&mapB, s.linv_tf32, tf32_rows(s.n), np, tf::BN, pair ? tfp::BK : tf::BK);
+  rc = make_map(&mapB, s.linv_tf32, tf32_rows(s.n), np, use_cluster ? tf::BN / 2 : tf::BN, pair ? tfp::BK : tf::BK);
   if (rc != BBO_OK) return rc;
   const int64_t tiles = qc_pad / tf::BM;
   const int64_t nblk = ceil_div(np, tf::BN);
@@ -1111,8 +1156,25 @@ static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
   if (nblk < 2) nsplit = 1;
   *nsplit_out = 4;   // k_acq always sums the four slots
   prof_begin(kProfTf32, st);
-  if (pair)
-    k_vnorm_tf32_pair<<<dim3(unsigned(tiles), unsigned(nsplit)), tf::THREADS, tfp::SMEM_BYTES, st>>>(
+  if (use_cluster) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(tiles), unsigned(nsplit));
+    cfg.blockDim = dim3(tf::THREADS);
+    cfg.dynamicSmemBytes = tfp::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const int np_i = int(np);
+    const int64_t qp_i = w.qp;
+    double* vp = w.vpart;
+    BBO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_vnorm_tf32_pair<2>, mapA, mapB, np_i, qp_i, vp));
+  } else if (pair)
+    k_vnorm_tf32_pair<1><<<dim3(unsigned(tiles), unsigned(nsplit)), tf::THREADS, tfp::SMEM_BYTES, st>>>(
         mapA, mapB, int(np), w.qp, w.vpart);
   else
     k_vnorm_tf32<<<dim3(unsigned(tiles), unsigned(nsplit)), tf::THREADS, tf::SMEM_BYTES, st>>>(mapA, mapB, int(np),
