@@ -499,6 +499,230 @@ k_vnorm_tf32_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------
+// 2-SM variant (tcgen05 cta_group::2): a CTA pair computes M = 256 candidates x N = 256 rows per
+// instruction.  Each CTA stages its own 128-candidate K* tile and only HALF (128 rows) of every
+// L^-1 tile; the tensor cores read the other half from the peer SM, so operand bytes ingested per
+// SM and per flop drop by a third versus k_vnorm_tf32_pair (that ingest, ~14 TB/s chip-wide, is
+// what bounds the 1-SM kernels).  Stages are 3 x 8 KB = 24 KB, 8 stages.
+//   * both CTAs run a TMA producer; all loads signal the LEADER's full barrier (count 2, each
+//     producer arrives with its own expect_tx, the peer remotely through mapa)
+//   * only the leader's warp 1 issues tcgen05.mma.cta_group::2; tcgen05.commit.cta_group::2
+//     multicasts the "stage free" / "accumulator full" arrivals to both CTAs
+//   * each CTA's epilogue drains its own TMEM half and arrives on the leader's "accumulator empty"
+//     barrier (count 256)
+// Row-block pairing, triangular bounds and accumulation slots are those of k_vnorm_tf32_pair.
+// ------------------------------------------------------------------------------------------
+namespace tf2 {
+constexpr int BM = 128, BN = 256, BK = 16, UK = 8, STAGES = 8;
+constexpr int A_BYTES = BM * BK * 4;            // 8 KB
+constexpr int BH_BYTES = (BN / 2) * BK * 4;     // 8 KB: this CTA's half of one L^-1 tile
+constexpr int STAGE_BYTES = A_BYTES + 2 * BH_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0,
+                                                int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(tf::smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mma_tf32_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(tf::smem_u32(bar)), "h"(uint16_t(3))
+               : "memory");
+}
+}  // namespace tf2
+
+__global__ void __launch_bounds__(tf::THREADS, 1)
+k_vnorm_tf32_2sm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int np,
+                 int64_t qc_pad, double* __restrict__ vpart) {
+  using namespace tf;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[tf2::STAGES], empty_bar[tf2::STAGES], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_base_sh;
+  uint32_t cta_rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  const bool leader = cta_rank == 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  const int c0 = blockIdx.x * tf2::BM;
+  const int nblk = (np + tf2::BN - 1) / tf2::BN;
+  const int S = gridDim.y;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < tf2::STAGES; ++s) {
+      mbar_init(&full_bar[s], 2);      // one arrive(+expect_tx) from each CTA's producer (used in the leader)
+      mbar_init(&empty_bar[s], 1);     // one multicast commit per phase
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 256);  // epilogue threads of both CTAs (used in the leader)
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {   // same warp id in both CTAs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_sh;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ===== TMA producer (both CTAs) =====
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int b0 = blockIdx.y; b0 < nblk; b0 += 2 * S) {
+        const int b1 = b0 + S;
+        const bool has1 = b1 < nblk;
+        const int kend0 = min((b0 + 1) * tf2::BN, np);
+        const int kend = has1 ? min((b1 + 1) * tf2::BN, np) : kend0;
+        for (int k = 0; k < kend; k += tf2::BK) {
+          const bool act0 = k < kend0;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = sgen + stage * tf2::STAGE_BYTES;
+          const uint32_t lbar = tf2::map_to_cta(smem_u32(&full_bar[stage]), 0);
+          tf2::mbar_expect_tx_cluster(
+              lbar, tf2::A_BYTES + (act0 ? tf2::BH_BYTES : 0) + (has1 ? tf2::BH_BYTES : 0));
+          tf2::tma_load_2d_2sm(sa, &mapA, lbar, k, c0);
+          if (act0)
+            tf2::tma_load_2d_2sm(sa + tf2::A_BYTES, &mapB, lbar, k, b0 * tf2::BN + int(cta_rank) * (tf2::BN / 2));
+          if (has1)
+            tf2::tma_load_2d_2sm(sa + tf2::A_BYTES + tf2::BH_BYTES, &mapB, lbar, k,
+                                 b1 * tf2::BN + int(cta_rank) * (tf2::BN / 2));
+          if (++stage == tf2::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {   // ===== MMA issuer (leader CTA only) =====
+      // D=f32, A=B=tf32, K-major, N=256, M=256 (two SMs)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(tf2::BN >> 3) << 17) | (uint32_t(256 >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int b0 = blockIdx.y; b0 < nblk; b0 += 2 * S) {
+        const int b1 = b0 + S;
+        const bool has1 = b1 < nblk;
+        const int kend0 = min((b0 + 1) * tf2::BN, np);
+        const int kend = has1 ? min((b1 + 1) * tf2::BN, np) : kend0;
+        mbar_wait(&tempty_bar[0], acc_phase ^ 1);
+        if (has1) mbar_wait(&tempty_bar[1], acc_phase ^ 1);
+        tc_fence_after();
+        for (int k = 0; k < kend; k += tf2::BK) {
+          const bool act0 = k < kend0;
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = sbase + stage * tf2::STAGE_BYTES;
+          const uint64_t adesc = tfp::make_desc64(sa);
+          if (act0) {
+            const uint64_t bdesc = tfp::make_desc64(sa + tf2::A_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < tf2::BK / tf2::UK; ++kk)
+              tf2::mma_tf32_2sm(tmem_base, adesc + uint64_t(kk * 2), bdesc + uint64_t(kk * 2), idesc,
+                                (k | kk) != 0 ? 1u : 0u);
+          }
+          if (has1) {
+            const uint64_t bdesc = tfp::make_desc64(sa + tf2::A_BYTES + tf2::BH_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < tf2::BK / tf2::UK; ++kk)
+              tf2::mma_tf32_2sm(tmem_base + uint32_t(tf2::BN), adesc + uint64_t(kk * 2), bdesc + uint64_t(kk * 2),
+                                idesc, (k | kk) != 0 ? 1u : 0u);
+          }
+          tf2::commit_2sm(&empty_bar[stage]);                        // frees the stage in both CTAs
+          if (k + tf2::BK == kend0) tf2::commit_2sm(&tfull_bar[0]);   // block b0 complete in both halves
+          if (++stage == tf2::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (has1) tf2::commit_2sm(&tfull_bar[1]);
+        acc_phase ^= 1;
+      }
+    }
+  } else {   // ===== epilogue (warps 2..5 of both CTAs) =====
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    double tot0 = 0.0, tot1 = 0.0, tot2 = 0.0, tot3 = 0.0;
+    uint32_t acc_phase = 0;
+    for (int b0 = blockIdx.y; b0 < nblk; b0 += 2 * S) {
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const int nb = b0 + a * S;
+        if (nb >= nblk) break;
+        mbar_wait(&tfull_bar[a], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(a * tf2::BN);
+        float part = 0.f;
+#pragma unroll 2
+        for (int c = 0; c < tf2::BN; c += 32) {
+          float v[32];
+          tmem_ld32(taddr + uint32_t(c), v);
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            s0 = fmaf(v[i], v[i], s0);
+            s1 = fmaf(v[i + 1], v[i + 1], s1);
+            s2 = fmaf(v[i + 2], v[i + 2], s2);
+            s3 = fmaf(v[i + 3], v[i + 3], s3);
+          }
+          part += (s0 + s1) + (s2 + s3);
+        }
+        const int slot = nb & 3;
+        if (slot == 0) tot0 += double(part);
+        else if (slot == 1) tot1 += double(part);
+        else if (slot == 2) tot2 += double(part);
+        else tot3 += double(part);
+        tc_fence_before();
+        tf2::mbar_arrive_cluster(tf2::map_to_cta(smem_u32(&tempty_bar[a]), 0));   // leader's barrier
+      }
+      acc_phase ^= 1;
+    }
+    const double tots[4] = {tot0, tot1, tot2, tot3};
+#pragma unroll
+    for (int g4 = 0; g4 < 4; ++g4)
+      if (g4 % S == int(blockIdx.y)) vpart[int64_t(g4) * qc_pad + c0 + row] = tots[g4];
+  }
+  tc_fence_before();
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // K* (qc_pad, np) float32 (TF32-rounded) and mu.  grid (qc_pad/64), 256 threads.
 // ------------------------------------------------------------------------------------------
 constexpr int kFC = 32, kFS = kFC + 1;
@@ -1132,13 +1356,16 @@ static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
   }
   const int64_t np = w.np;
   static const bool pair = getenv("BBO_TF32_SINGLE") == nullptr;    // paired row blocks by default
-  static const bool clus = getenv("BBO_TF32_NO_CLUSTER") == nullptr; // 2-CTA clusters with TMA multicast
+  static const bool clus = getenv("BBO_TF32_NO_CLUSTER") == nullptr; // 2-CTA clusters
+  static const bool two_sm = getenv("BBO_TF32_NO_2SM") == nullptr;   // cta_group::2 MMA (else TMA multicast)
   static bool attr2 = false;
   if (pair && !attr2) {
     BBO_CUDA_CHECK(cudaFuncSetAttribute(k_vnorm_tf32_pair<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         tfp::SMEM_BYTES));
     BBO_CUDA_CHECK(cudaFuncSetAttribute(k_vnorm_tf32_pair<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         tfp::SMEM_BYTES));
+    BBO_CUDA_CHECK(cudaFuncSetAttribute(k_vnorm_tf32_2sm, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        tf2::SMEM_BYTES));
     attr2 = true;
   }
   const bool use_cluster = pair && clus && (qc_pad / tf::BM) % 2 == 0;
@@ -1160,7 +1387,7 @@ static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(unsigned(tiles), unsigned(nsplit));
     cfg.blockDim = dim3(tf::THREADS);
-    cfg.dynamicSmemBytes = tfp::SMEM_BYTES;
+    cfg.dynamicSmemBytes = two_sm ? tf2::SMEM_BYTES : tfp::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -1172,7 +1399,10 @@ static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
     const int np_i = int(np);
     const int64_t qp_i = w.qp;
     double* vp = w.vpart;
-    BBO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_vnorm_tf32_pair<2>, mapA, mapB, np_i, qp_i, vp));
+    if (two_sm)
+      BBO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_vnorm_tf32_2sm, mapA, mapB, np_i, qp_i, vp));
+    else
+      BBO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_vnorm_tf32_pair<2>, mapA, mapB, np_i, qp_i, vp));
   } else if (pair)
     k_vnorm_tf32_pair<1><<<dim3(unsigned(tiles), unsigned(nsplit)), tf::THREADS, tfp::SMEM_BYTES, st>>>(
         mapA, mapB, int(np), w.qp, w.vpart);
