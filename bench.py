@@ -361,11 +361,11 @@ def run_b200(a):
             lib.bbo_profile_enable(0)
             opeak = live_matmul_peak(torch.float64, False) if otag == "vnorm" else live_matmul_peak(torch.float32, True, n=8192)
             oach = float(a.n) * a.n * q / (otot * 1e-3) / 1e12
-            other["roofline"] = {"bound": "tensor", "kernel": "k_vnorm (DMMA.8x8x4)" if otag == "vnorm" else "k_vnorm_tf32 (tcgen05)",
+            other["roofline"] = {"bound": "tensor", "kernel": "k_vnorm (DMMA.8x8x4)" if otag == "vnorm" else "k_vnorm_tf32_2sm (tcgen05)",
                                  "achieved": oach, "peak": opeak, "unit": "TFLOP/s", "frac": oach / opeak,
                                  "launches_timed": oreg}
         share = tot_ms / max(tot_ms + ktot + stot, 1e-9)
-        roof = {"bound": "tensor", "kernel": "k_vnorm (DMMA.8x8x4)" if tag == "vnorm" else "k_vnorm_tf32 (tcgen05.mma kind::tf32)",
+        roof = {"bound": "tensor", "kernel": "k_vnorm (DMMA.8x8x4)" if tag == "vnorm" else "k_vnorm_tf32_2sm (tcgen05.mma cta_group::2 kind::tf32)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "launches_timed": regions, "avg_launch_ms": avg_ms,
                 "algorithmic_flops_per_launch": flops_per_launch, "share_of_step": share,
