@@ -14,6 +14,36 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(); }
+void add_launches(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// Executable graphs retired by fit_adam: destroyed lazily, once the event recorded after their last
+// launch has completed (checked on the next retire call) -- never while launches are pending.
+struct Retired {
+  cudaGraphExec_t exec;
+  cudaGraph_t graph;
+  cudaEvent_t done;
+};
+static std::vector<Retired> g_retired;
+void retire_graph(cudaGraphExec_t exec, cudaGraph_t graph, cudaStream_t st) {
+  for (size_t i = 0; i < g_retired.size();) {
+    if (cudaEventQuery(g_retired[i].done) == cudaSuccess) {
+      cudaGraphExecDestroy(g_retired[i].exec);
+      cudaGraphDestroy(g_retired[i].graph);
+      cudaEventDestroy(g_retired[i].done);
+      g_retired[i] = g_retired.back();
+      g_retired.pop_back();
+    } else {
+      ++i;
+    }
+  }
+  cudaGetLastError();   // cudaEventQuery returns cudaErrorNotReady for pending work
+  Retired r{exec, graph, nullptr};
+  if (cudaEventCreateWithFlags(&r.done, cudaEventDisableTiming) == cudaSuccess) {
+    cudaEventRecord(r.done, st);
+    g_retired.push_back(r);
+  }
+}
 
 struct ProfState {
   bool enabled = false;
@@ -21,6 +51,7 @@ struct ProfState {
   size_t used[kProfTags] = {0};
 };
 static ProfState g_prof;
+bool prof_enabled() { return g_prof.enabled; }
 constexpr size_t kProfMaxEvents = 1 << 14;
 static cudaEvent_t prof_event(int tag) {
   auto& v = g_prof.ev[tag];

@@ -42,6 +42,11 @@ enum ProfTag {
   kProfTf32 = 6,    // TF32 scoring panel (tcgen05)
   kProfTags = 8
 };
+bool prof_enabled();
+long long launch_count();
+void add_launches(long long n);
+// destroys an executable graph once everything enqueued on `st` so far has completed
+void retire_graph(cudaGraphExec_t exec, cudaGraph_t graph, cudaStream_t st);
 void prof_begin(int tag, cudaStream_t st);
 void prof_end(int tag, cudaStream_t st);
 

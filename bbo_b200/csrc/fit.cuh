@@ -19,6 +19,7 @@ struct FitWorkspace {
   double* sum_alpha = nullptr;  // (batch)
   double* gpart = nullptr;    // (batch, ntp, d+1) gradient tile partials
   double* hyp = nullptr;      // (batch, 2d+2)
+  int64_t* step_dev = nullptr;  // (batch) Adam step counters (device resident: graph replay)
 
   static size_t bytes(int64_t n, int64_t d, int64_t batch);
   int bind(void* ws, size_t ws_bytes, int64_t n, int64_t d, int64_t batch);
