@@ -20,6 +20,7 @@ struct FitWorkspace {
   double* gpart = nullptr;    // (batch, ntp, d+1) gradient tile partials
   double* hyp = nullptr;      // (batch, 2d+2)
   int64_t* step_dev = nullptr;  // (batch) Adam step counters (device resident: graph replay)
+  double* side = nullptr;     // (batch, 2, 64, 64) un-solved copies of the tile below the diagonal block
 
   static size_t bytes(int64_t n, int64_t d, int64_t batch);
   int bind(void* ws, size_t ws_bytes, int64_t n, int64_t d, int64_t batch);

@@ -1134,6 +1134,197 @@ k_kstar_mma(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const uint32_
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// K* producer, second form (default).  Same 3xTF32 mma.sync contraction, but the contraction is
+// AUGMENTED by two columns so that the tensor core returns the finished exponent / distance:
+//   RBF     a = [log2e * a', A', 1, 0..]   b = [b, 1, B', 0..]   a.b = log2(s2) - log2e/2 |a'-b|^2
+//           with A' = log2(s2) - log2e/2 |a'|^2, B' = -log2e/2 |b|^2        ->  k = ex2(a.b)
+//   Matern  a = [-2 a', |a'|^2, 1, 0..]    b = [b, 1, |b|^2, 0..] a.b = |a'-b|^2
+// For d = 20 the two columns live in the zero padding of the 8-wide k-steps, so they are free.
+// Padded observations carry B' = -1e4 (|b|^2 = 1e8): their K* is exactly 0 without a predicate.
+// B fragments come from ldmatrix.x4 (hi/lo x two k-halves per instruction; the b16 view of a row of
+// four 32-bit words hands lane (g,t) word t of row g, which is the tf32 B fragment), ex2 is the bare
+// MUFU.  Per 16x8 output tile: 3*KS HMMA + KS LDSM + 1 LDS.64 + 4 MUFU + 4 CVT + 4 FFMA + 2 STG.64
+// (the first form issued ~110 instructions per tile; ncu in profiles/).
+// ------------------------------------------------------------------------------------------
+constexpr int kMma2MaxD = 126;
+
+__global__ void __launch_bounds__(256)
+k_prescale_aug(const double* __restrict__ X, int64_t n, int64_t np, int d, int dk, int matern,
+               const double* __restrict__ hyp, const double* __restrict__ alpha, uint32_t* __restrict__ Xhi,
+               uint32_t* __restrict__ Xlo, float* __restrict__ alpha32) {
+  const int64_t j = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= np) return;
+  float acc = 0.f;
+  for (int k = lane; k < d; k += 32) {
+    const float v = (j < n) ? float(X[j * d + k] * hyp[d + k]) : 0.f;
+    uint32_t hi, lo;
+    split_tf32(v, hi, lo);
+    Xhi[j * dk + k] = hi;
+    Xlo[j * dk + k] = lo;
+    acc = fmaf(v, v, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  for (int k = d + lane; k < dk; k += 32) {
+    float v = 0.f;
+    if (k == d) v = 1.f;
+    else if (k == d + 1) v = (j < n) ? (matern ? acc : -0.5f * 1.4426950408889634f * acc) : (matern ? 1e8f : -1e4f);
+    uint32_t hi, lo;
+    split_tf32(v, hi, lo);
+    Xhi[j * dk + k] = hi;
+    Xlo[j * dk + k] = lo;
+  }
+  if (lane == 0) alpha32[j] = (j < n) ? float(alpha[j]) : 0.f;
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, unsigned addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+
+template <typename T1, int KS, bool MATERN>   // KS = ceil((d+2)/8) k-steps
+__global__ void __launch_bounds__(256)
+k_kstar_mma2(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const uint32_t* __restrict__ Xhi,
+             const uint32_t* __restrict__ Xlo, int64_t np, const double* __restrict__ hyp,
+             const float* __restrict__ alpha32, float* __restrict__ Ks, double* __restrict__ mu) {
+  constexpr int DK = KS * 8;
+  constexpr int LS = 4 * ((DK / 4 + 1) | 1);   // LS/4 odd: ldmatrix rows hit distinct 16-byte bank groups
+  extern __shared__ __align__(16) uint32_t msm2[];
+  uint32_t* bhi = msm2;                  // 2 x 64 x LS
+  uint32_t* blo = bhi + 2 * 64 * LS;     // 2 x 64 x LS
+  float* als = reinterpret_cast<float*>(blo + 2 * 64 * LS);   // 2 x 64
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int d = h.d;
+  const float eps = MATERN ? float(h.pairwise_eps) : 0.f;
+  const float s2 = float(hyp[2 * d]);
+  const float kLog2e = 1.4426950408889634f;
+  const float l2s2 = __log2f(s2);
+  const int64_t row0 = int64_t(blockIdx.x) * 128 + warp * 16;   // this warp's 16 candidates
+
+  // A fragments: a0 (g, t), a1 (g+8, t), a2 (g, t+4), a3 (g+8, t+4) per k-step; a' = xq/l - eps
+  uint32_t ahi[KS][4], alo[KS][4];
+  {
+    float av[KS][4];
+    float an0 = 0.f, an1 = 0.f;   // |a'|^2 of rows g and g+8
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        const int64_t r = row0 + g + ((f & 1) ? 8 : 0);
+        const int k = ks * 8 + t + ((f & 2) ? 4 : 0);
+        float v = 0.f;
+        if (k < d) {
+          const double x = (r < qc) ? double(Xq[r * d + k]) : 0.0;
+          v = float(x * hyp[d + k]) - eps;
+        }
+        av[ks][f] = v;
+        if (f & 1) an1 = fmaf(v, v, an1);
+        else an0 = fmaf(v, v, an0);
+      }
+    an0 += __shfl_xor_sync(0xffffffffu, an0, 1);
+    an0 += __shfl_xor_sync(0xffffffffu, an0, 2);
+    an1 += __shfl_xor_sync(0xffffffffu, an1, 1);
+    an1 += __shfl_xor_sync(0xffffffffu, an1, 2);
+    const float R0 = MATERN ? an0 : fmaf(-0.5f * kLog2e, an0, l2s2);
+    const float R1 = MATERN ? an1 : fmaf(-0.5f * kLog2e, an1, l2s2);
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        const int k = ks * 8 + t + ((f & 2) ? 4 : 0);
+        float u = 0.f;
+        if (k < d) u = (MATERN ? -2.f : kLog2e) * av[ks][f];
+        else if (k == d) u = (f & 1) ? R1 : R0;
+        else if (k == d + 1) u = 1.f;
+        split_tf32(u, ahi[ks][f], alo[ks][f]);
+      }
+  }
+
+  auto tload = [&](int64_t j0, int buf) {
+    constexpr int CH = DK / 4;   // 16-byte chunks per row
+    for (int c = tid; c < 64 * CH * 2; c += 256) {
+      const int arr = c / (64 * CH), rem = c % (64 * CH), r = rem / CH, ch = rem % CH;
+      const uint32_t* src = (arr ? Xlo : Xhi) + (j0 + r) * DK + ch * 4;
+      uint32_t* dst = (arr ? blo : bhi) + (buf * 64 + r) * LS + ch * 4;
+      const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(dst));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src));
+    }
+    if (tid < 64) als[buf * 64 + tid] = alpha32[j0 + tid];
+    asm volatile("cp.async.commit_group;");
+  };
+  tload(0, 0);
+  // ldmatrix lane address: matrices 0/1 = hi (k 0-3, 4-7), 2/3 = lo; lane supplies row (lane & 7)
+  const unsigned lane_addr =
+      static_cast<unsigned>(__cvta_generic_to_shared((lane & 16) ? blo : bhi)) +
+      unsigned(((lane & 7) * LS + ((lane >> 3) & 1) * 4) * 4);
+  float m0 = 0.f, m1 = 0.f;   // mu partials of rows g, g+8
+  const int ntile = int(np / 64);
+  float* o0 = Ks + (row0 + g) * np + 2 * t;
+  float* o1 = Ks + (row0 + g + 8) * np + 2 * t;
+  for (int tl = 0; tl < ntile; ++tl) {
+    const int buf = tl & 1;
+    asm volatile("cp.async.wait_group 0;");
+    __syncthreads();                                   // tile tl visible; everyone is done with tile tl-1
+    if (tl + 1 < ntile) tload(int64_t(tl + 1) * 64, buf ^ 1);
+    const unsigned tb = lane_addr + unsigned(buf * 64 * LS * 4);
+    const float* ap = als + buf * 64 + 2 * t;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t h0, h1, l0, l1;
+        ldsm_x4(h0, h1, l0, l1, tb + unsigned((nt * 8 * LS + ks * 8) * 4));
+        mma_tf32_16x8x8(c, alo[ks], h0, h1);
+        mma_tf32_16x8x8(c, ahi[ks], l0, l1);
+        mma_tf32_16x8x8(c, ahi[ks], h0, h1);
+      }
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (!MATERN) {
+          v[e] = ex2_approx(fminf(c[e], l2s2));
+        } else {
+          const float r = 2.2360679775f * sqrtf(fmaxf(c[e], 0.f));
+          v[e] = s2 * fmaf(r, fmaf(r, 1.f / 3.f, 1.f), 1.f) * ex2_approx(-kLog2e * r);
+        }
+      }
+      const float2 al = *reinterpret_cast<const float2*>(ap + nt * 8);
+      m0 = fmaf(v[0], al.x, fmaf(v[1], al.y, m0));
+      m1 = fmaf(v[2], al.x, fmaf(v[3], al.y, m1));
+      uint32_t u[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u[e]) : "f"(v[e]));
+      *reinterpret_cast<uint2*>(o0 + nt * 8) = make_uint2(u[0], u[1]);
+      *reinterpret_cast<uint2*>(o1 + nt * 8) = make_uint2(u[2], u[3]);
+    }
+    o0 += 64;
+    o1 += 64;
+  }
+  m0 += __shfl_xor_sync(0xffffffffu, m0, 1);
+  m0 += __shfl_xor_sync(0xffffffffu, m0, 2);
+  m1 += __shfl_xor_sync(0xffffffffu, m1, 1);
+  m1 += __shfl_xor_sync(0xffffffffu, m1, 2);
+  if (t == 0) {
+    mu[row0 + g] = hyp[2 * d + 1] + double(m0);
+    mu[row0 + g + 8] = hyp[2 * d + 1] + double(m1);
+  }
+}
+
+template <int KS>
+static size_t kstar_mma2_smem() {
+  constexpr int DK = KS * 8, LS = 4 * ((DK / 4 + 1) | 1);
+  return sizeof(uint32_t) * (size_t(4) * 64 * LS) + sizeof(float) * 128;
+}
+
 template <int KS>
 static size_t kstar_mma_smem() {
   constexpr int DK = KS * 8, LS = 4 * ((DK / 4 + 1) | 1);
@@ -1188,7 +1379,7 @@ size_t score_tf32_extra_bytes(int64_t n, int64_t d, int64_t qp) {
   const int64_t np = padded(n);
   return 2 * align256(size_t(qp) * np * sizeof(float)) + align256(size_t(qp) * sizeof(double)) +
          align256(size_t(np) * d * sizeof(float)) + 2 * align256(size_t(np) * sizeof(float)) +
-         2 * align256(size_t(np) * (d + 8) * sizeof(uint32_t)) + 256;
+         2 * align256(size_t(np) * (d + 16) * sizeof(uint32_t)) + 256;
 }
 
 static Tf32Scratch carve(const ScoreWorkspace& w, int64_t d) {
@@ -1209,7 +1400,7 @@ static Tf32Scratch carve(const ScoreWorkspace& w, int64_t d) {
   t.alpha32 = reinterpret_cast<float*>(p);
   p += align256(size_t(w.np) * sizeof(float));
   t.Xhi = reinterpret_cast<uint32_t*>(p);
-  p += align256(size_t(w.np) * (d + 8) * sizeof(uint32_t));
+  p += align256(size_t(w.np) * (d + 16) * sizeof(uint32_t));
   t.Xlo = reinterpret_cast<uint32_t*>(p);
   return t;
 }
@@ -1274,7 +1465,60 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
   const int64_t np = w.np;
   prof_begin(kProfKstar, st);
   static const bool use_mma = getenv("BBO_KSTAR_NO_MMA") == nullptr;
-  if (use_mma && s.h.d <= kMmaMaxD) {
+  static const bool use_v1 = getenv("BBO_KSTAR_V1") != nullptr;
+  if (use_mma && !use_v1 && s.h.d <= kMma2MaxD) {
+    const int ks = (s.h.d + 2 + 7) / 8;
+    const unsigned grid = unsigned(qc_pad / 128);
+    const bool matern = s.h.kind == BBO_KERNEL_MATERN52;
+#define BBO_KSTAR_MMA2_L(T_, KS_, M_)                                                                          \
+  k_kstar_mma2<T_, KS_, M_><<<grid, 256, sm, st>>>(s.h, static_cast<const T_*>(Xq), qc, t.Xhi, t.Xlo, np, s.hyp, \
+                                                   t.alpha32, t.Ks[buf], t.mu[buf])
+#define BBO_KSTAR_MMA2(KS_)                                                                                    \
+  case KS_: {                                                                                                  \
+    const size_t sm = kstar_mma2_smem<KS_>();                                                                  \
+    static bool attr_set = false;                                                                              \
+    if (!attr_set && sm > 48 * 1024) {                                                                         \
+      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_mma2<float, KS_, false>,                                     \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));              \
+      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_mma2<float, KS_, true>,                                      \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));              \
+      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_mma2<double, KS_, false>,                                    \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));              \
+      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_mma2<double, KS_, true>,                                     \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));              \
+      attr_set = true;                                                                                         \
+    }                                                                                                          \
+    if (xq_is_f32) {                                                                                           \
+      if (matern) BBO_KSTAR_MMA2_L(float, KS_, true);                                                          \
+      else BBO_KSTAR_MMA2_L(float, KS_, false);                                                                \
+    } else {                                                                                                   \
+      if (matern) BBO_KSTAR_MMA2_L(double, KS_, true);                                                         \
+      else BBO_KSTAR_MMA2_L(double, KS_, false);                                                               \
+    }                                                                                                          \
+  } break;
+    switch (ks) {
+      BBO_KSTAR_MMA2(1)
+      BBO_KSTAR_MMA2(2)
+      BBO_KSTAR_MMA2(3)
+      BBO_KSTAR_MMA2(4)
+      BBO_KSTAR_MMA2(5)
+      BBO_KSTAR_MMA2(6)
+      BBO_KSTAR_MMA2(7)
+      BBO_KSTAR_MMA2(8)
+      BBO_KSTAR_MMA2(9)
+      BBO_KSTAR_MMA2(10)
+      BBO_KSTAR_MMA2(11)
+      BBO_KSTAR_MMA2(12)
+      BBO_KSTAR_MMA2(13)
+      BBO_KSTAR_MMA2(14)
+      BBO_KSTAR_MMA2(15)
+      BBO_KSTAR_MMA2(16)
+      default:
+        return BBO_ERR_BAD_ARG;
+    }
+#undef BBO_KSTAR_MMA2
+#undef BBO_KSTAR_MMA2_L
+  } else if (use_mma && s.h.d <= kMmaMaxD) {
     const int ks = (s.h.d + 7) / 8;
     const unsigned grid = unsigned(qc_pad / 128);
 #define BBO_KSTAR_MMA(KS_)                                                                                     \
@@ -1435,7 +1679,14 @@ int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const vo
   const size_t esz = xq_is_f32 ? sizeof(float) : sizeof(double);
   const int d = s.h.d;
   static const bool use_mma = getenv("BBO_KSTAR_NO_MMA") == nullptr;
-  if (use_mma && d <= kMmaMaxD) {
+  static const bool use_v1 = getenv("BBO_KSTAR_V1") != nullptr;
+  if (use_mma && !use_v1 && d <= kMma2MaxD) {
+    const int dk = 8 * ((d + 2 + 7) / 8);
+    k_prescale_aug<<<unsigned(ceil_div(w.np, 8)), 256, 0, st>>>(s.X, s.n, w.np, d, dk,
+                                                               s.h.kind == BBO_KERNEL_MATERN52 ? 1 : 0, s.hyp, s.alpha,
+                                                               t.Xhi, t.Xlo, t.alpha32);
+    BBO_LAUNCH_CHECK();
+  } else if (use_mma && d <= kMmaMaxD) {
     const int dk = 8 * ((d + 7) / 8);
     k_prescale_split<<<unsigned(ceil_div(w.np, 8)), 256, 0, st>>>(s.X, s.n, w.np, d, dk, s.hyp, s.alpha, t.Xhi, t.Xlo,
                                                                  t.bnorm, t.alpha32);
