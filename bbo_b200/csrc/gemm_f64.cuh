@@ -111,6 +111,29 @@ __device__ __forceinline__ void gemm_nt_mainloop(const double* __restrict__ A, i
   __syncthreads();
 }
 
+// One BK-wide step of the product from a staged tile pair (the body of the main loop above), for
+// kernels that run their own (persistent, cross-tile) pipeline.
+template <class Cfg>
+__device__ __forceinline__ void gemm_compute_stage(const double* __restrict__ st, Acc<Cfg>& acc) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = warp / Cfg::WARPS_N, wn = warp % Cfg::WARPS_N;
+  const int g = lane >> 2, t = lane & 3;
+  const double* as = st + (wm * Cfg::WM + g) * Cfg::LDS + t;
+  const double* bs = st + Cfg::BM * Cfg::LDS + (wn * Cfg::WN + g) * Cfg::LDS + t;
+#pragma unroll
+  for (int kk = 0; kk < Cfg::BK / 4; ++kk) {
+    double a[Cfg::MF], b[Cfg::NF];
+#pragma unroll
+    for (int i = 0; i < Cfg::MF; ++i) a[i] = as[i * 8 * Cfg::LDS + kk * 4];
+#pragma unroll
+    for (int j = 0; j < Cfg::NF; ++j) b[j] = bs[j * 8 * Cfg::LDS + kk * 4];
+#pragma unroll
+    for (int i = 0; i < Cfg::MF; ++i)
+#pragma unroll
+      for (int j = 0; j < Cfg::NF; ++j) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i], b[j]);
+  }
+}
+
 // Calls f(row, col, v0, v1) for every accumulator pair: (row, col) and (row, col+1) are tile-
 // relative coordinates of v0 and v1.
 template <class Cfg, class F>
