@@ -21,6 +21,7 @@ ACQ_EI, ACQ_UCB, ACQ_PI = 0, 1, 2
 PREC_FP64, PREC_TF32 = 0, 1
 ROW_ALIGN = 128
 TOPK_MAX = 128
+APPEND_MAX = 32
 HOST_STAGE_CHUNKS = 4
 
 
@@ -66,6 +67,8 @@ SIGNATURES = {
                                   _D, _D, _P, _P, _P, _SZ, _P]),
     "bbo_gp_theta_to_hyp": (C.c_int, [_I64, _I64, _I32, _I32, _P, _P, _P]),
     "bbo_gp_factorize": (C.c_int, [C.POINTER(GpHyper), _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "bbo_gp_append_workspace_bytes": (_SZ, [_I64, _I64]),
+    "bbo_gp_append": (C.c_int, [C.POINTER(GpHyper), _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "bbo_gp_make_tf32": (C.c_int, [_I64, _P, _P, _P]),
     "bbo_gp_predict": (C.c_int, [C.POINTER(GpState), _P, _I64, _P, _P, _P, _P, _SZ, _I64, _P]),
     "bbo_acq_eval": (C.c_int, [C.POINTER(Acq), _P, _P, _P, _I64, _I32, _P]),

@@ -133,6 +133,19 @@ int bbo_cov_matrix(const bbo_gp_hyper* h, const double* hyp_dev, const double* X
   return cov_matrix(*h, hyp_dev, X1_dev, q, X2_dev, n, out_dev, ldo, 0.0, S(stream));
 }
 
+size_t bbo_gp_append_workspace_bytes(int64_t n_old, int64_t m) {
+  if (n_old < 1 || m < 1 || m > BBO_APPEND_MAX) return 0;
+  return append_workspace_bytes(n_old, m);
+}
+int bbo_gp_append(const bbo_gp_hyper* h, int64_t n_old, int64_t m, const double* X_dev, const double* y_dev,
+                  const double* hyp_dev, double* linv_dev, double* alpha_dev, double* logdet_dev,
+                  int32_t* info_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  if (!hyper_ok(h) || n_old < 1 || m < 1 || m > BBO_APPEND_MAX) return BBO_ERR_BAD_SHAPE;
+  if (!X_dev || !y_dev || !hyp_dev || !linv_dev || !alpha_dev || !info_dev || !workspace_dev) return BBO_ERR_BAD_ARG;
+  return gp_append(*h, n_old, m, X_dev, y_dev, hyp_dev, linv_dev, alpha_dev, logdet_dev, info_dev, workspace_dev,
+                   workspace_bytes, S(stream));
+}
+
 int bbo_gp_fit_value_grad(const bbo_gp_hyper* h, int64_t n, int64_t batch, const double* X_dev,
                           const double* y_dev, const double* hyp_dev, double* value_dev, double* grad_dev,
                           int32_t* info_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {

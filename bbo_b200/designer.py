@@ -13,6 +13,13 @@ data model is out of scope; ``INTEGRATION.md`` shows how to plug the same pieces
 ``BODesigner``); the default surrogate is ``CudaGP`` (the reference's default ``GPyTorchGP`` is
 third-party, SURVEY F3) trained with ``sign=-1`` (maximising the likelihood, as GPyTorchGP does);
 ``suggest(count)`` honours ``count`` (the reference ignores it after initialisation, bo.py:117).
+
+Opt-in extensions (the defaults keep the reference's refit-from-scratch behaviour):
+  ``warm_start=True``   the new surrogate starts Adam from the previous suggestion's hyper-parameters
+                        instead of the factory's initial values (bo.py:105 builds a fresh model each time).
+  ``refit_every=k``     hyper-parameters are refitted only at every k-th suggestion; in between, new
+                        observations are appended to the factorised state (``CudaGP.append``: O(m n^2)
+                        instead of epochs x O(n^3)).
 """
 from __future__ import annotations
 
@@ -36,12 +43,22 @@ def default_surrogate_factory(train_X: torch.Tensor, train_Y: torch.Tensor, devi
                   lr=0.05, epochs=60, sign=-1.0)
 
 
+def _copy_parameters(src, dst) -> None:
+    """Warm start: previous fit's raw mean / kernel parameters -> the new surrogate's modules."""
+    for a, b in ((src._mean_module, dst._mean_module), (src._cov_module, dst._cov_module)):
+        pa, pb = dict(a.named_parameters()), dict(b.named_parameters())
+        with torch.no_grad():
+            for name, p in pb.items():
+                if name in pa and pa[name].shape == p.shape:
+                    p.copy_(pa[name].to(p.dtype))
+
+
 class B200BODesigner:
     def __init__(self, bounds, goal: str = "minimize", *, num_init: int = 10, seed: Optional[int] = None,
                  device="cuda", surrogate_factory: Callable = default_surrogate_factory,
                  acquisition_function_factory: Callable = lambda Y: EI(float(Y.max())),
                  acquisition_optimizer_factory: Callable = lambda rng: PoolOptimizer(8192, int(rng.integers(1 << 31))),
-                 precision: str = "fp64"):
+                 precision: str = "fp64", warm_start: bool = False, refit_every: int = 1):
         self.bounds = np.asarray(bounds, dtype=np.float64).reshape(-1, 2)
         self.d = self.bounds.shape[0]
         if goal not in ("minimize", "maximize"):
@@ -57,6 +74,12 @@ class B200BODesigner:
         self._X = np.zeros((0, self.d))
         self._y = np.zeros((0,))
         self.last_surrogate = None
+        if refit_every < 1:
+            raise ValueError("refit_every must be >= 1")
+        self._warm_start = bool(warm_start)
+        self._refit_every = int(refit_every)
+        self._since_fit = 0          # suggestions served by the current hyper-parameters
+        self._n_in_surrogate = 0     # observations the current surrogate has seen
 
     # converters/core.py:211-216: features scaled to [0,1]
     def _to_unit(self, X):
@@ -72,8 +95,20 @@ class B200BODesigner:
         X = torch.as_tensor(self._to_unit(self._X))
         y = torch.as_tensor(self._y if self.goal == "maximize" else -self._y).reshape(-1, 1)   # bo.py:80-83
         Y = (y - y.mean(dim=0)) / (y.std(dim=0) + 1e-6)                                      # bo.py:126-128
-        surrogate = self._surrogate_factory(X, Y, self._device)
-        surrogate.train()
+        prev = self.last_surrogate
+        n_seen = self._n_in_surrogate
+        if (prev is not None and hasattr(prev, "append") and self._since_fit + 1 < self._refit_every
+                and len(self._y) >= n_seen):
+            surrogate = prev                     # same hyper-parameters, enlarged data set
+            surrogate.append(X[n_seen:], Y[n_seen:], Y_all=Y)
+            self._since_fit += 1
+        else:
+            surrogate = self._surrogate_factory(X, Y, self._device)
+            if self._warm_start and prev is not None:
+                _copy_parameters(prev, surrogate)
+            surrogate.train()
+            self._since_fit = 0
+        self._n_in_surrogate = len(self._y)
         acqf = self._acqf_factory(Y)
         score_fn = TensorScoreFn(surrogate, acqf, self._precision)
         best, scores, _ = self._optimizer.optimize_tensor(score_fn, self.d, count=count)

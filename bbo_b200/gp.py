@@ -264,6 +264,68 @@ class CudaGP(Surrogate):
                           linv=linv.data_ptr(), alpha=alpha.data_ptr(), linv_tf32=None)
         self._state = {"st": st, "hyp": hyp, "linv": linv, "alpha": alpha, "logdet": None, "linv_tf32": None}
 
+    # ------------------------------------------------------------------ incremental update
+    def append(self, X_new: torch.Tensor, Y_new: torch.Tensor, *, Y_all: Optional[torch.Tensor] = None) -> None:
+        """Add observations WITHOUT refitting the hyper-parameters: the factorised state
+        (L^-1, alpha) is extended by ``bbo_gp_append`` in O(m n^2) instead of the O(n^3) refactorisation
+        (and instead of the reference's full refit, bo.py:101-106).  The result is the state the full
+        factorisation of the enlarged data set would give with the current hyper-parameters.
+        ``Y_all`` (n+m,1), if given, replaces ALL labels (BODesigner re-standardises the labels at every
+        suggestion, bo.py:126-128; L^-1 does not depend on them and alpha is recomputed from scratch).
+        Opt-in: call ``train()`` whenever the hyper-parameters should follow the data again."""
+        _check_2d("X_new", X_new)
+        _check_2d("Y_new", Y_new)
+        if X_new.shape[1] != self.d or Y_new.shape != (X_new.shape[0], 1):
+            raise ValueError(f"expected X_new (m,{self.d}) and Y_new (m,1), got {tuple(X_new.shape)}, "
+                             f"{tuple(Y_new.shape)}")
+        xn = _as_2d_f64(X_new, self._device)
+        yn = _as_2d_f64(Y_new, self._device).reshape(-1)
+        if Y_all is not None:
+            _check_2d("Y_all", Y_all)
+            if Y_all.shape != (self.n + xn.shape[0], 1):
+                raise ValueError(f"Y_all must be ({self.n + xn.shape[0]},1), got {tuple(Y_all.shape)}")
+            y_all = _as_2d_f64(Y_all, self._device).reshape(-1)
+            self._Y = y_all[:self.n].contiguous()
+            yn = y_all[self.n:].contiguous()
+        if xn.shape[0] == 0:
+            return
+        s = self._ensure_state()
+        with torch.cuda.device(self._device):
+            for a in range(0, xn.shape[0], _lib.APPEND_MAX):
+                xb, yb = xn[a:a + _lib.APPEND_MAX], yn[a:a + _lib.APPEND_MAX]
+                m, n_old = xb.shape[0], self.n
+                X_all = torch.cat([self._X, xb]).contiguous()
+                Y_all = torch.cat([self._Y, yb]).contiguous()
+                np_new = int(self._lib.bbo_padded_n(n_old + m))
+                linv, alpha = s["linv"], s["alpha"]
+                if np_new != self.np:      # re-lay out: old block top-left, unit diagonal on the new padding
+                    big = torch.zeros(np_new, np_new, dtype=_F64, device=self._device)
+                    big[:self.np, :self.np] = linv
+                    big.diagonal()[self.np:] = 1.0
+                    linv = big
+                    alpha = torch.zeros(np_new, dtype=_F64, device=self._device)
+                info = torch.zeros(1, dtype=torch.int32, device=self._device)
+                ws = self._workspace("append", int(self._lib.bbo_gp_append_workspace_bytes(n_old, m)))
+                h = self._hyper()
+                _lib.check(self._lib.bbo_gp_append(
+                    C.byref(h), n_old, m, _lib.ptr(X_all), _lib.ptr(Y_all), _lib.ptr(s["hyp"]), _lib.ptr(linv),
+                    _lib.ptr(alpha), _lib.ptr(s["logdet"]), _lib.ptr(info), _lib.ptr(ws), ws.numel(),
+                    _lib.stream_ptr(self._device)), "bbo_gp_append")
+                i = int(info.item())
+                if i != 0:
+                    self._state = None
+                    _raise_not_pd(i)
+                self._X, self._Y = X_all, Y_all
+                self.n, self.np = n_old + m, np_new
+                st = _lib.GpState(h=h, n=self.n, X=self._X.data_ptr(), hyp=s["hyp"].data_ptr(),
+                                  linv=linv.data_ptr(), alpha=alpha.data_ptr(), linv_tf32=None)
+                s = {"st": st, "hyp": s["hyp"], "linv": linv, "alpha": alpha, "logdet": s["logdet"],
+                     "linv_tf32": None}
+                self._state = s
+            if self._q_chunk_auto:
+                self._q_chunk = default_q_chunk(self.n)
+            self._ws.pop("fit", None)      # sized for the old n
+
     # ------------------------------------------------------------------ predict
     def predict_diag(self, query_X: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """Per-candidate posterior mean and variance, float64 (q,), (q,)."""

@@ -10,6 +10,8 @@
  *   bbo_gp_fit_adam         bbo/algorithms/surrogates/gp/gp.py:54-63 (GP.train loop)
  *   bbo_gp_factorize        bbo/algorithms/surrogates/gp/objectives.py:20-31
  *                           (solve_gp_linear_system, cached at gp/gp.py:66-74)
+ *   bbo_gp_append           designers/bo/bo.py:101-106 (the refit after update(): rebuilt state
+ *                           for the enlarged data set, hyper-parameters kept)
  *   bbo_gp_predict          bbo/algorithms/surrogates/gp/gp.py:75-83 (GP.predict)
  *   bbo_gp_score_pool       gp/gp.py:75-83 + designers/bo/acquisitions.py:18-31
  *                           + shared/trial.py:278-294 (get_best_trials), i.e. the
@@ -68,6 +70,7 @@ typedef enum bbo_precision { BBO_PREC_FP64 = 0, BBO_PREC_TF32 = 1 } bbo_precisio
 
 #define BBO_ROW_ALIGN 128   /* n is padded to a multiple of this in all n x n buffers */
 #define BBO_TOPK_MAX 128
+#define BBO_APPEND_MAX 32   /* observations appended per bbo_gp_append call */
 #define BBO_HOST_STAGE_CHUNKS 4   /* bbo_gp_score_pool_host copies this many chunks per H2D transfer */
 
 int bbo_version(void);
@@ -162,6 +165,21 @@ int bbo_gp_factorize(const bbo_gp_hyper* h, int64_t n, int64_t batch, const doub
                      const double* y_dev, const double* hyp_dev, double* linv_dev,
                      double* alpha_dev, double* chol_dev, double* logdet_dev, int32_t* info_dev,
                      void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---- incremental update: append observations to a factorised problem (hyper-parameters kept) ----
+ * Replaces the from-scratch refit of designers/bo/bo.py:101-106 between two hyper-parameter fits:
+ * O(m n^2) (four passes over L^-1) instead of O(n^3).  Opt-in: the reference has no counterpart.
+ *   X (n_old+m, d), y (n_old+m): ALL observations, the m new ones last; 1 <= m <= BBO_APPEND_MAX.
+ *   linv (np', np'), np' = bbo_padded_n(n_old+m): on entry L^-1 of the first n_old observations in its
+ *        leading block, zero elsewhere except a unit diagonal on rows >= n_old (exactly what
+ *        bbo_gp_factorize leaves when np' == bbo_padded_n(n_old); otherwise the caller re-lays it out);
+ *        on exit L^-1 of all n_old+m observations (same layout).
+ *   alpha (np') is recomputed; logdet (may be NULL) is incremented by the new pivots' logs.
+ *   info[0] = j+1 if the leading minor j (j >= n_old) is not positive definite.                      */
+size_t bbo_gp_append_workspace_bytes(int64_t n_old, int64_t m);
+int bbo_gp_append(const bbo_gp_hyper* h, int64_t n_old, int64_t m, const double* X_dev, const double* y_dev,
+                  const double* hyp_dev, double* linv_dev, double* alpha_dev, double* logdet_dev,
+                  int32_t* info_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ---- fitted state used by predict / score (all dev pointers, one problem) ------------- */
 typedef struct bbo_gp_state {
