@@ -6,6 +6,8 @@ GradientFreeOptimizer plug-in points.  No CPU fallback.
 """
 from .acquisitions import EI, PI, UCB  # noqa: F401
 from .gp import CudaGP, cov_matrix  # noqa: F401
-from .kernels import ConstantMean, Matern52Kernel, RBFKernel, ScaleKernel, TemplateKernel  # noqa: F401
+from .kernels import (ConstantMean, KumarWarp, Matern52Kernel, MLPBlock, MLPMean, MLPWarp, RBFKernel,  # noqa: F401
+                      ScaleKernel, TemplateKernel, WarpKernel)
+from .warped import CudaWarpedGP, surrogate  # noqa: F401
 
 __version__ = "0.1.0"

@@ -157,6 +157,21 @@ int bbo_gp_fit_value_grad(const bbo_gp_hyper* h, int64_t n, int64_t batch, const
   return fit_value_grad(*h, w, X_dev, y_dev, hyp_dev, value_dev, grad_dev, info_dev, S(stream));
 }
 
+int bbo_gp_fit_value_grad_inputs(const bbo_gp_hyper* h, int64_t n, const double* X_dev, const double* y_dev,
+                                 const double* hyp_dev, double* value_dev, double* grad_dev, double* gradX_dev,
+                                 double* grady_dev, int32_t* info_dev, void* workspace_dev,
+                                 size_t workspace_bytes, void* stream) {
+  if (!hyper_ok(h) || n < 1) return BBO_ERR_BAD_SHAPE;
+  if (!X_dev || !y_dev || !hyp_dev || !value_dev || !grad_dev || !gradX_dev || !grady_dev || !info_dev)
+    return BBO_ERR_BAD_ARG;
+  FitWorkspace w;
+  int rc = w.bind(workspace_dev, workspace_bytes, n, h->d, 1);
+  if (rc != BBO_OK) return rc;
+  rc = fit_value_grad(*h, w, X_dev, y_dev, hyp_dev, value_dev, grad_dev, info_dev, S(stream));
+  if (rc != BBO_OK) return rc;
+  return fit_grad_inputs(*h, w, X_dev, gradX_dev, grady_dev, S(stream));
+}
+
 int bbo_gp_fit_adam(const bbo_gp_hyper* h, int64_t n, int64_t batch, int32_t ard, int32_t has_scale,
                     const double* X_dev, const double* y_dev, double* theta_dev, double* adam_m_dev,
                     double* adam_v_dev, int64_t step0, int64_t epochs, double lr, double sign,
@@ -314,6 +329,13 @@ int bbo_topk_merge(const double* score_dev, const int64_t* index_dev, int64_t m,
                    double* out_score_dev, int64_t* out_index_dev, void* stream) {
   if (!score_dev || !index_dev || !out_score_dev || !out_index_dev) return BBO_ERR_BAD_ARG;
   return topk_merge(score_dev, index_dev, m, k, out_score_dev, out_index_dev, S(stream));
+}
+
+int bbo_warp_kumaraswamy(const void* x_dev, int64_t count, double a, double b, double eps, void* out_dev,
+                         int32_t is_f32, void* stream) {
+  if (count < 0 || !(a > 0.0) || !(b > 0.0)) return BBO_ERR_BAD_ARG;
+  if (count > 0 && (!x_dev || !out_dev)) return BBO_ERR_BAD_ARG;
+  return warp_kumar(x_dev, count, a, b, eps, out_dev, is_f32, S(stream));
 }
 
 int bbo_pool_uniform(uint64_t seed, int64_t row_offset, int64_t q, int64_t d, void* out_dev, int32_t is_f32,

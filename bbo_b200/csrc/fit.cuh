@@ -37,6 +37,8 @@ int fit_adam(const bbo_gp_hyper& h, const FitWorkspace& w, int ard, int has_scal
              double lr, double sign, double* values, int32_t* info, cudaStream_t st);
 int theta_to_hyp(int64_t d, int64_t batch, int ard, int has_scale, const double* theta, double* hyp,
                  cudaStream_t st);
+int fit_grad_inputs(const bbo_gp_hyper& h, const FitWorkspace& w, const double* X, double* gradX, double* grady,
+                    cudaStream_t st);
 size_t append_workspace_bytes(int64_t n_old, int64_t m);
 int gp_append(const bbo_gp_hyper& h, int64_t n, int64_t m, const double* X, const double* y, const double* hyp,
               double* linv, double* alpha, double* logdet, int32_t* info, void* ws, size_t ws_bytes,

@@ -50,4 +50,30 @@ int pool_uniform(uint64_t seed, int64_t row_offset, int64_t q, int64_t d, void* 
   return BBO_OK;
 }
 
+// Kumaraswamy input warp of a candidate pool (gp/warpers.py:52-65), the prologue of scoring when the
+// covariance is a WarpKernel(KumarWarp): out = 1 - (1 - clip(x, eps, 1-eps)^a)^b, computed in float64,
+// one pass over the pool (read once, written once).
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_warp_kumar(const T* __restrict__ x, int64_t count, double a, double b, double eps, T* __restrict__ out) {
+  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= count) return;
+  double v = double(x[i]);
+  v = fmin(fmax(v, eps), 1.0 - eps);      // NaN stays NaN (torch.clip propagates it too)
+  out[i] = T(1.0 - pow(1.0 - pow(v, a), b));
+}
+
+int warp_kumar(const void* x, int64_t count, double a, double b, double eps, void* out, int is_f32,
+               cudaStream_t st) {
+  if (count <= 0) return BBO_OK;
+  if (is_f32)
+    k_warp_kumar<float><<<unsigned(ceil_div(count, 256)), 256, 0, st>>>(static_cast<const float*>(x), count, a, b, eps,
+                                                                       static_cast<float*>(out));
+  else
+    k_warp_kumar<double><<<unsigned(ceil_div(count, 256)), 256, 0, st>>>(static_cast<const double*>(x), count, a, b,
+                                                                        eps, static_cast<double*>(out));
+  BBO_LAUNCH_CHECK();
+  return BBO_OK;
+}
+
 }  // namespace bbo

@@ -42,6 +42,8 @@ int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const vo
 int make_tf32(int64_t n, const double* linv, float* out, cudaStream_t st);
 int64_t tf32_rows(int64_t n);
 
+int warp_kumar(const void* x, int64_t count, double a, double b, double eps, void* out, int is_f32,
+               cudaStream_t st);
 int pool_uniform(uint64_t seed, int64_t row_offset, int64_t q, int64_t d, void* out, int is_f32, cudaStream_t st);
 
 }  // namespace bbo

@@ -74,7 +74,10 @@ class _Theta:
 
 
 def _hyper(kind: int, d: int, eps: float, noise: float) -> _lib.GpHyper:
-    return _lib.GpHyper(kind=kind, d=d, pairwise_eps=eps, noise=noise)
+    # The reference adds ``torch.eye(n) * noise_variance`` (objectives.py:28, gp.py:82): a float32 tensor, so
+    # the noise that reaches its float64 K is float32(noise).  Reproduced here (|rel. change| <= 6e-8).
+    noise32 = float(torch.tensor(noise, dtype=torch.float32))
+    return _lib.GpHyper(kind=kind, d=d, pairwise_eps=eps, noise=noise32)
 
 
 def _raise_not_pd(info: int):

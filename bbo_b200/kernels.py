@@ -72,6 +72,109 @@ class ConstantMean(nn.Module):
         return self.constant.expand(*X.shape[:-1], 1)
 
 
+# ---------------------------------------------------------------------------------------------
+# Input warps and the learned mean.  Same constructor signatures, attribute names and
+# forward arithmetic as the reference (state dicts interchange); they are tiny differentiable torch
+# modules evaluated on the GPU -- the O(n^3) objective / O(n^2 q) posterior they feed is the CUDA
+# library (``bbo_b200.warped.CudaWarpedGP``).
+# ---------------------------------------------------------------------------------------------
+class MLPBlock(nn.Module):
+    """warpers.py:8-28: Linear -> [norm] -> activation -> [dropout]."""
+
+    def __init__(self, in_d: int, out_d: int, norm=nn.BatchNorm1d, activation=nn.ReLU, dropout: float = 0.1,
+                 bias: bool = True):
+        super().__init__()
+        mlp = [nn.Linear(in_d, out_d, bias)]
+        if norm is not None:
+            mlp.append(norm(out_d))
+        mlp.append(activation())
+        if dropout > 0:
+            mlp.append(nn.Dropout(dropout))
+        self.mlp = nn.Sequential(*mlp)
+
+    def forward(self, X: torch.Tensor) -> torch.Tensor:
+        return self.mlp(X)
+
+
+class MLPWarp(nn.Module):
+    """warpers.py:31-49."""
+
+    def __init__(self, in_d: int, hidden_d, norm=None, activation=nn.Tanh, dropout: float = 0.0,
+                 bias: bool = True):
+        super().__init__()
+        layers = []
+        for h in hidden_d:
+            layers.append(MLPBlock(in_d, h, norm, activation, dropout, bias))
+            in_d = h
+        self.layers = nn.Sequential(*layers)
+
+    def forward(self, X: torch.Tensor) -> torch.Tensor:
+        return self.layers(X)
+
+
+class KumarWarp(nn.Module):
+    """warpers.py:52-65: Kumaraswamy CDF 1 - (1 - x^a)^b on inputs clipped to [1e-6, 1 - 1e-6],
+    a = softplus(alpha), b = softplus(beta)."""
+
+    def __init__(self):
+        super().__init__()
+        self.alpha = nn.Parameter(torch.zeros(1))
+        self.beta = nn.Parameter(torch.zeros(1))
+        self.eps = 1e-6
+
+    def forward(self, X: torch.Tensor) -> torch.Tensor:
+        X = X.clip(self.eps, 1 - self.eps)
+        a = torch.nn.functional.softplus(self.alpha)
+        b = torch.nn.functional.softplus(self.beta)
+        return 1 - (1 - X.pow(a)).pow(b)
+
+
+class MLPMean(nn.Module):
+    """means.py:28-35: mean(X) = Linear(in_d, 1)(warp_module(X))."""
+
+    def __init__(self, in_d: int, warp_module: nn.Module):
+        super().__init__()
+        self.warp_module = warp_module
+        self.mean = nn.Linear(in_d, 1)
+
+    def forward(self, X: torch.Tensor) -> torch.Tensor:
+        return self.mean(self.warp_module(X))
+
+
+class WarpKernel(nn.Module):
+    """kernels.py:59-68: K(X1, X2) = base_kernel(warp(X1), warp(X2))."""
+
+    def __init__(self, base_kernel: nn.Module, warp_module: nn.Module):
+        super().__init__()
+        self.warp_module = warp_module
+        self.base_kernel = base_kernel
+
+    def forward(self, X1: torch.Tensor, X2: torch.Tensor) -> torch.Tensor:
+        return self.base_kernel(self.warp_module(X1), self.warp_module(X2))
+
+
+def split_warps(cov_module: nn.Module):
+    """Peels WarpKernel layers off a covariance module (ours or the reference's, duck-typed):
+    returns (warp modules in application order, (kind, eps, raw_lengthscale, raw_variance) of the rest).
+    ScaleKernel(WarpKernel(base, w)) and WarpKernel(ScaleKernel(base), w) are both accepted."""
+    warps = []
+    raw_var = None
+    m = cov_module
+    while True:
+        if hasattr(m, "warp_module") and hasattr(m, "base_kernel"):
+            warps.append(m.warp_module)
+            m = m.base_kernel
+        elif hasattr(m, "base_kernel") and hasattr(m, "variance"):
+            if raw_var is not None:
+                raise TypeError("nested ScaleKernels are not supported")
+            raw_var = m.variance
+            m = m.base_kernel
+        else:
+            break
+    kind, eps, raw_ls, _ = describe_cov(m)
+    return warps, (kind, eps, raw_ls, raw_var)
+
+
 def describe_cov(cov_module: nn.Module):
     """(kind, pairwise_eps, raw_lengthscale Parameter, raw_variance Parameter | None).
 
@@ -83,7 +186,7 @@ def describe_cov(cov_module: nn.Module):
         raw_var = cov_module.variance
         base = cov_module.base_kernel
     if hasattr(base, "warp_module"):
-        raise NotImplementedError("WarpKernel is not on the CUDA path (SURVEY section 8 row N4)")
+        raise NotImplementedError("WarpKernel needs bbo_b200.warped.CudaWarpedGP (or bbo_b200.surrogate(...))")
     if not hasattr(base, "lengthscale") or not hasattr(base, "impl"):
         raise TypeError(f"unsupported covariance module {type(cov_module).__name__}")
     impl = base.impl
@@ -96,5 +199,5 @@ def describe_cov(cov_module: nn.Module):
 
 def describe_mean(mean_module: nn.Module):
     if not hasattr(mean_module, "constant"):
-        raise NotImplementedError("only ConstantMean is on the CUDA path (SURVEY section 8 row N4)")
+        raise NotImplementedError("a learned mean needs bbo_b200.warped.CudaWarpedGP (or bbo_b200.surrogate(...))")
     return mean_module.constant

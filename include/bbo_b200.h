@@ -7,6 +7,8 @@
  *
  *   bbo_gp_fit_value_grad   bbo/algorithms/surrogates/gp/objectives.py:34-45 (value)
  *                           + loss.backward() at gp/gp.py:62 (gradient)
+ *   bbo_gp_fit_value_grad_inputs  the same + autograd's gradient w.r.t. cov inputs / targets
+ *                           (WarpKernel gp/kernels.py:59-68, MLPMean gp/means.py:28-35)
  *   bbo_gp_fit_adam         bbo/algorithms/surrogates/gp/gp.py:54-63 (GP.train loop)
  *   bbo_gp_factorize        bbo/algorithms/surrogates/gp/objectives.py:20-31
  *                           (solve_gp_linear_system, cached at gp/gp.py:66-74)
@@ -131,6 +133,16 @@ int bbo_gp_fit_value_grad(const bbo_gp_hyper* h, int64_t n, int64_t batch, const
                           const double* y_dev, const double* hyp_dev, double* value_dev,
                           double* grad_dev, int32_t* info_dev, void* workspace_dev,
                           size_t workspace_bytes, void* stream);
+
+/* Same for ONE problem, plus the gradients w.r.t. the inputs and the targets:
+ *   gradX (n,d) = d value / d X,  grady (n) = d value / d y = -K^-1 (y - c).
+ * These are what autograd needs to train an input warp (WarpKernel with KumarWarp / MLPWarp,
+ * gp/kernels.py:59-68, gp/warpers.py:31-65) or a learned mean (MLPMean, gp/means.py:28-35) on top
+ * of this library: X is then warp(X) and y is Y - mean(X) (pass c = 0 in hyp).                   */
+int bbo_gp_fit_value_grad_inputs(const bbo_gp_hyper* h, int64_t n, const double* X_dev, const double* y_dev,
+                                 const double* hyp_dev, double* value_dev, double* grad_dev,
+                                 double* gradX_dev, double* grady_dev, int32_t* info_dev,
+                                 void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ---- train: GP.train (gp.py:54-63) entirely on the device ----------------------------
  * theta (batch, P) raw parameters in the reference's Adam order (gp.py:55):
@@ -259,6 +271,12 @@ int bbo_topk_merge(const double* score_dev, const int64_t* index_dev, int64_t m,
  * sharding of the pool produces the same candidates.  is_f32 selects float/double output.  */
 int bbo_pool_uniform(uint64_t seed, int64_t row_offset, int64_t q, int64_t d, void* out_dev,
                      int32_t is_f32, void* stream);
+
+/* Kumaraswamy input warp (gp/warpers.py:52-65) of `count` values, the scoring prologue for a
+ * WarpKernel(KumarWarp) covariance: out = 1 - (1 - clip(x, eps, 1-eps)^a)^b with a, b already
+ * softplus-transformed; in place allowed (out_dev == x_dev).                                       */
+int bbo_warp_kumaraswamy(const void* x_dev, int64_t count, double a, double b, double eps, void* out_dev,
+                         int32_t is_f32, void* stream);
 
 #ifdef __cplusplus
 }
