@@ -8,7 +8,7 @@
 //
 //   B  = k(X_new, X_old)            (m x n)      cov_matrix (k_cov_rect)
 //   S  = B L^-T                     (m x n)      k_rows_dot     one pass over L^-1
-//   Lc = chol(C + noise I - S S^T)  (m x m)      k_append_schur one CTA
+//   Lc = chol(C + noise I - S S^T)  (m x m)      k_append_gram + k_append_schur (one CTA)
 //   R  = -Lc^-1 (S L^-1)            (m x n)      k_cols_dot_partial / k_cols_finish: one pass over L^-1
 //   z  = L'^-1 (y - c),  alpha = L'^-T z         the same two kernels with one vector
 //
@@ -24,58 +24,97 @@ constexpr int kAppMax = BBO_APPEND_MAX;   // new rows per call
 constexpr int kAppMB = 8;                 // vectors per register pass
 constexpr int kAppRC = 512;               // rows of L^-1 per partial-sum chunk
 
-// out[i][r] = sum_{k <= min(r, kcap-1)} V[i][k] * W[r][k]  for r in [0, nrows): one warp per row r.
+// out[i][r] = sum_{k <= min(r, kcap-1)} V[i][k] * W[r][k]  for r in [0, nrows).
+// One warp per FOUR consecutive rows (W is zero above its diagonal, so all four contract k <= r+3): every
+// V value loaded serves four rows, which keeps the V traffic (m vectors, L2 resident) at 2 m/4 of the W bytes.
+constexpr int kAppRW = 4;
 __global__ void __launch_bounds__(256)
 k_rows_dot(const double* __restrict__ W, int64_t ld, int64_t nrows, int64_t kcap, const double* __restrict__ V,
            int64_t ldv, int m, double* __restrict__ out, int64_t ldo) {
-  const int64_t r = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int64_t r = (int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5)) * kAppRW;
   const int lane = threadIdx.x & 31;
   if (r >= nrows) return;
-  const int64_t kend = (r + 1 < kcap) ? r + 1 : kcap;
+  const int64_t rl = (r + kAppRW <= nrows) ? r + kAppRW : nrows;      // rows [r, rl)
+  const int64_t kend = (rl < kcap) ? rl : kcap;
   const double* w = W + r * ld;
   for (int i0 = 0; i0 < m; i0 += kAppMB) {
-    double acc[kAppMB];
+    double acc[kAppRW][kAppMB];
 #pragma unroll
-    for (int i = 0; i < kAppMB; ++i) acc[i] = 0.0;
+    for (int u = 0; u < kAppRW; ++u)
+#pragma unroll
+      for (int i = 0; i < kAppMB; ++i) acc[u][i] = 0.0;
+#pragma unroll 2
     for (int64_t k = lane; k < kend; k += 32) {
-      const double wv = w[k];
+      double wv[kAppRW], vv[kAppMB];
 #pragma unroll
-      for (int i = 0; i < kAppMB; ++i)
-        if (i0 + i < m) acc[i] = fma(V[int64_t(i0 + i) * ldv + k], wv, acc[i]);
+      for (int u = 0; u < kAppRW; ++u) wv[u] = (r + u < rl) ? w[u * ld + k] : 0.0;
+#pragma unroll
+      for (int i = 0; i < kAppMB; ++i) vv[i] = (i0 + i < m) ? V[int64_t(i0 + i) * ldv + k] : 0.0;
+#pragma unroll
+      for (int u = 0; u < kAppRW; ++u)
+#pragma unroll
+        for (int i = 0; i < kAppMB; ++i) acc[u][i] = fma(vv[i], wv[u], acc[u][i]);
     }
 #pragma unroll
-    for (int i = 0; i < kAppMB; ++i) {
-      double a = acc[i];
+    for (int u = 0; u < kAppRW; ++u)
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      if (lane == 0 && i0 + i < m) out[int64_t(i0 + i) * ldo + r] = a;
-    }
+      for (int i = 0; i < kAppMB; ++i) {
+        double a = acc[u][i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0 && i0 + i < m && r + u < rl) out[int64_t(i0 + i) * ldo + r + u] = a;
+      }
   }
 }
 
-// P[rc][i][j] = sum_{r in chunk rc, r >= j, r < nrows} Sv[i][r] * W[r][j]; thread per column j.
-// grid (ceil(ncols/128), ceil(nrows/kAppRC)), 128 threads.
-__global__ void __launch_bounds__(128)
+// P[rc][i][j] = sum_{r in chunk rc, r >= j, r < nrows} Sv[i][r] * W[r][j].
+// grid (ceil(ncols/128), ceil(nrows/kAppRC)), 512 threads = 4 row groups x 128 columns: thread (g, c) walks
+// rows r0 + g, r0 + g + 4, ... of column jb + c with eight independent loads in flight; the four groups
+// are combined through shared memory in a fixed order.
+__global__ void __launch_bounds__(512)
 k_cols_dot_partial(const double* __restrict__ W, int64_t ld, int64_t nrows, int64_t ncols,
                    const double* __restrict__ Sv, int64_t lds, int m, double* __restrict__ P, int64_t ldp) {
-  const int64_t j = int64_t(blockIdx.x) * 128 + threadIdx.x;
+  __shared__ double red[3][kAppMB][128];
+  const int c = threadIdx.x & 127, g = threadIdx.x >> 7;
+  const int64_t jb = int64_t(blockIdx.x) * 128, j = jb + c;
   const int64_t r0 = int64_t(blockIdx.y) * kAppRC;
   const int64_t r1 = (r0 + kAppRC < nrows) ? r0 + kAppRC : nrows;
-  const int64_t jb = int64_t(blockIdx.x) * 128;    // first column of this CTA: rows below it are all zero
+  const int64_t rs = (r0 > jb ? r0 : jb) + g;      // rows above the CTA's first column hold only zeros
+  const bool live = j < ncols;
   for (int i0 = 0; i0 < m; i0 += kAppMB) {
     double acc[kAppMB];
 #pragma unroll
     for (int i = 0; i < kAppMB; ++i) acc[i] = 0.0;
-    if (j < ncols) {
-      for (int64_t r = (r0 > jb ? r0 : jb); r < r1; ++r) {
-        const double wv = W[r * ld + j];      // zero above the diagonal (r < j)
+    if (live) {
+      int64_t r = rs;
+      for (; r + 28 < r1; r += 32) {
+        double wv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) wv[u] = W[(r + 4 * u) * ld + j];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int i = 0; i < kAppMB; ++i)
+            if (i0 + i < m) acc[i] = fma(Sv[int64_t(i0 + i) * lds + r + 4 * u], wv[u], acc[i]);
+      }
+      for (; r < r1; r += 4) {
+        const double wv = W[r * ld + j];
 #pragma unroll
         for (int i = 0; i < kAppMB; ++i)
           if (i0 + i < m) acc[i] = fma(Sv[int64_t(i0 + i) * lds + r], wv, acc[i]);
       }
+    }
+    __syncthreads();
+    if (g > 0) {
+#pragma unroll
+      for (int i = 0; i < kAppMB; ++i) red[g - 1][i][c] = acc[i];
+    }
+    __syncthreads();
+    if (g == 0 && live) {
 #pragma unroll
       for (int i = 0; i < kAppMB; ++i)
-        if (i0 + i < m) P[(int64_t(blockIdx.y) * m + i0 + i) * ldp + j] = acc[i];
+        if (i0 + i < m)
+          P[(int64_t(blockIdx.y) * m + i0 + i) * ldp + j] = ((acc[i] + red[0][i][c]) + red[1][i][c]) + red[2][i][c];
     }
   }
 }
@@ -115,25 +154,45 @@ k_cols_finish(const double* __restrict__ P, int64_t ldp, int nchunk, int m, int6
   }
 }
 
+// Gram[i][j] = sum_r S[i][r] S[j][r] (j <= i): one CTA per pair, fixed-order block reduction.
+__global__ void __launch_bounds__(256)
+k_append_gram(const double* __restrict__ S, int64_t lds, int64_t n, int m, double* __restrict__ Gram) {
+  __shared__ double sh[8];
+  const int i = blockIdx.x / m, j = blockIdx.x % m;
+  if (j > i) return;
+  double a0 = 0.0, a1 = 0.0;
+  int64_t r = threadIdx.x;
+  for (; r + 256 < n; r += 512) {
+    a0 = fma(S[int64_t(i) * lds + r], S[int64_t(j) * lds + r], a0);
+    a1 = fma(S[int64_t(i) * lds + r + 256], S[int64_t(j) * lds + r + 256], a1);
+  }
+  if (r < n) a0 = fma(S[int64_t(i) * lds + r], S[int64_t(j) * lds + r], a0);
+  double a = a0 + a1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    Gram[blockIdx.x] = t;
+  }
+}
+
 // One CTA: Cs = C + noise I - S S^T (lower), Lc = chol(Cs), Lci = Lc^-1 -> Lci (m x m, row-major, zeros
 // above) and the diagonal block of linv; logdet += sum log Lc_ii; info = n + j + 1 on a non-positive pivot.
 __global__ void __launch_bounds__(256)
-k_append_schur(const double* __restrict__ Kx, int64_t ldk, const double* __restrict__ S, int64_t lds, int64_t n,
+k_append_schur(const double* __restrict__ Kx, int64_t ldk, const double* __restrict__ Gram, int64_t n,
                int m, double noise, double* __restrict__ Lci, double* __restrict__ linv, int64_t ld,
                double* __restrict__ logdet, int32_t* __restrict__ info) {
   __shared__ double A[kAppMax][kAppMax + 1];
   __shared__ double Iv[kAppMax][kAppMax + 1];
   __shared__ int fail;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x;
   if (tid == 0) fail = 0;
-  for (int p = warp; p < m * m; p += 8) {
-    const int i = p / m, j = p % m;
-    if (j > i) continue;
-    double a = 0.0;
-    for (int64_t r = lane; r < n; r += 32) a = fma(S[int64_t(i) * lds + r], S[int64_t(j) * lds + r], a);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0) A[i][j] = Kx[int64_t(i) * ldk + n + j] + (i == j ? noise : 0.0) - a;
+  for (int e = tid; e < m * m; e += 256) {
+    const int i = e / m, j = e % m;
+    if (j <= i) A[i][j] = Kx[int64_t(i) * ldk + n + j] + (i == j ? noise : 0.0) - Gram[e];
   }
   __syncthreads();
   // unblocked right-looking Cholesky (m <= 32): thread (i) owns row i
@@ -182,7 +241,7 @@ __global__ void k_resid(const double* __restrict__ y, const double* __restrict__
 }
 
 struct AppendWs {
-  double *Kx, *S, *Lci, *resid, *z, *P;
+  double *Kx, *S, *Lci, *Gram, *resid, *z, *P;
   int64_t ldp;
   int nchunk;
 };
@@ -190,7 +249,7 @@ static size_t a256(size_t b) { return (b + 255) / 256 * 256; }
 size_t append_workspace_bytes(int64_t n_old, int64_t m) {
   const int64_t nt = n_old + m, np = padded(nt);
   const int64_t nchunk = ceil_div(np, kAppRC);
-  return a256(size_t(m) * nt * 8) + a256(size_t(m) * np * 8) + a256(size_t(m) * m * 8) + 2 * a256(size_t(np) * 8) +
+  return a256(size_t(m) * nt * 8) + a256(size_t(m) * np * 8) + 2 * a256(size_t(m) * m * 8) + 2 * a256(size_t(np) * 8) +
          a256(size_t(nchunk) * m * np * 8) + 256;
 }
 
@@ -208,6 +267,8 @@ int gp_append(const bbo_gp_hyper& h, int64_t n, int64_t m, const double* X, cons
   p += a256(size_t(m) * np * 8);
   w.Lci = reinterpret_cast<double*>(p);
   p += a256(size_t(m) * m * 8);
+  w.Gram = reinterpret_cast<double*>(p);
+  p += a256(size_t(m) * m * 8);
   w.resid = reinterpret_cast<double*>(p);
   p += a256(size_t(np) * 8);
   w.z = reinterpret_cast<double*>(p);
@@ -220,14 +281,16 @@ int gp_append(const bbo_gp_hyper& h, int64_t n, int64_t m, const double* X, cons
   int rc = cov_matrix(h, hyp, X + n * d, m, X, nt, w.Kx, nt, 0.0, st);
   if (rc != BBO_OK) return rc;
   // S = B L^-T
-  k_rows_dot<<<unsigned(ceil_div(n, 8)), 256, 0, st>>>(linv, np, n, n, w.Kx, nt, int(m), w.S, np);
+  k_rows_dot<<<unsigned(ceil_div(n, 8 * kAppRW)), 256, 0, st>>>(linv, np, n, n, w.Kx, nt, int(m), w.S, np);
   BBO_LAUNCH_CHECK();
-  k_append_schur<<<1, 256, 0, st>>>(w.Kx, nt, w.S, np, n, int(m), h.noise, w.Lci, linv, np, logdet, info);
+  k_append_gram<<<unsigned(m * m), 256, 0, st>>>(w.S, np, n, int(m), w.Gram);
+  BBO_LAUNCH_CHECK();
+  k_append_schur<<<1, 256, 0, st>>>(w.Kx, nt, w.Gram, n, int(m), h.noise, w.Lci, linv, np, logdet, info);
   BBO_LAUNCH_CHECK();
   // R = -Lc^-1 (S L^-1) -> rows [n, n+m) of linv, columns [0, n)
   {
     const int nch = int(ceil_div(n, kAppRC));
-    k_cols_dot_partial<<<dim3(unsigned(ceil_div(n, 128)), unsigned(nch)), 128, 0, st>>>(linv, np, n, n, w.S, np,
+    k_cols_dot_partial<<<dim3(unsigned(ceil_div(n, 128)), unsigned(nch)), 512, 0, st>>>(linv, np, n, n, w.S, np,
                                                                                      int(m), w.P, w.ldp);
     BBO_LAUNCH_CHECK();
     k_cols_finish<<<unsigned(ceil_div(n, 128)), 128, 0, st>>>(w.P, w.ldp, nch, int(m), n, w.Lci, 0, linv, np, n);
@@ -236,11 +299,11 @@ int gp_append(const bbo_gp_hyper& h, int64_t n, int64_t m, const double* X, cons
   // alpha = L'^-T L'^-1 (y - c)
   k_resid<<<unsigned(ceil_div(nt, 256)), 256, 0, st>>>(y, hyp, int(d), nt, w.resid);
   BBO_LAUNCH_CHECK();
-  k_rows_dot<<<unsigned(ceil_div(nt, 8)), 256, 0, st>>>(linv, np, nt, nt, w.resid, nt, 1, w.z, np);
+  k_rows_dot<<<unsigned(ceil_div(nt, 8 * kAppRW)), 256, 0, st>>>(linv, np, nt, nt, w.resid, nt, 1, w.z, np);
   BBO_LAUNCH_CHECK();
   {
     const int nch = int(ceil_div(nt, kAppRC));
-    k_cols_dot_partial<<<dim3(unsigned(ceil_div(nt, 128)), unsigned(nch)), 128, 0, st>>>(linv, np, nt, nt, w.z, np,
+    k_cols_dot_partial<<<dim3(unsigned(ceil_div(nt, 128)), unsigned(nch)), 512, 0, st>>>(linv, np, nt, nt, w.z, np,
                                                                                       1, w.P, w.ldp);
     BBO_LAUNCH_CHECK();
     k_cols_finish<<<unsigned(ceil_div(nt, 128)), 128, 0, st>>>(w.P, w.ldp, nch, 1, nt, w.Lci, 1, alpha, 0, 0);

@@ -50,6 +50,18 @@ void retire_graph(cudaGraphExec_t exec, cudaGraph_t graph, cudaStream_t st);
 void prof_begin(int tag, cudaStream_t st);
 void prof_end(int tag, cudaStream_t st);
 
+// cudaFuncSetAttribute (opt-in shared memory) applies to the CURRENT device only: one flag per device.
+struct DeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   // D(8x8) += A(8x4, row) * B(4x8, col); SASS: DMMA.8x8x4

@@ -402,16 +402,15 @@ int ScoreWorkspace::bind(void* ws, size_t ws_bytes, int64_t n, int64_t d, int64_
   return BBO_OK;
 }
 
-static bool g_attr_done = false;
+static DeviceOnce g_attr_once;
 static int set_smem_attrs() {
-  if (g_attr_done) return BBO_OK;
+  if (!g_attr_once.first()) return BBO_OK;
   BBO_CUDA_CHECK(cudaFuncSetAttribute(k_vnorm, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(Cfg128x64::SMEM_BYTES)));
   BBO_CUDA_CHECK(cudaFuncSetAttribute(k_vstore, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(Cfg64x64::SMEM_BYTES)));
   BBO_CUDA_CHECK(cudaFuncSetAttribute(k_cov_sub, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(Cfg64x64::SMEM_BYTES)));
-  g_attr_done = true;
   return BBO_OK;
 }
 

@@ -1476,8 +1476,8 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
 #define BBO_KSTAR_MMA2(KS_)                                                                                    \
   case KS_: {                                                                                                  \
     const size_t sm = kstar_mma2_smem<KS_>();                                                                  \
-    static bool attr_set = false;                                                                              \
-    if (!attr_set && sm > 48 * 1024) {                                                                         \
+    static DeviceOnce attr_once;                                                                               \
+    if (sm > 48 * 1024 && attr_once.first()) {                                                                 \
       BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_mma2<float, KS_, false>,                                     \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));              \
       BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_mma2<float, KS_, true>,                                      \
@@ -1486,7 +1486,6 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));              \
       BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_mma2<double, KS_, true>,                                     \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)));              \
-      attr_set = true;                                                                                         \
     }                                                                                                          \
     if (xq_is_f32) {                                                                                           \
       if (matern) BBO_KSTAR_MMA2_L(float, KS_, true);                                                          \
@@ -1524,13 +1523,12 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
 #define BBO_KSTAR_MMA(KS_)                                                                                     \
   case KS_: {                                                                                                  \
     const size_t sm = kstar_mma_smem<KS_>();                                                                   \
-    static bool attr_set = false;                                                                              \
-    if (!attr_set && sm > 48 * 1024) {                                                                         \
+    static DeviceOnce attr_once;                                                                               \
+    if (sm > 48 * 1024 && attr_once.first()) {                                                                 \
       BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_mma<float, KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           int(sm)));                                                           \
       BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_mma<double, KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           int(sm)));                                                           \
-      attr_set = true;                                                                                         \
     }                                                                                                          \
     if (xq_is_f32)                                                                                             \
       k_kstar_mma<float, KS_><<<grid, 256, sm, st>>>(s.h, static_cast<const float*>(Xq), qc, t.Xhi, t.Xlo,      \
@@ -1593,24 +1591,21 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
 
 static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf32Scratch& t, int buf,
                         int64_t qc_pad, int* nsplit_out, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.first())
     BBO_CUDA_CHECK(cudaFuncSetAttribute(k_vnorm_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, tf::SMEM_BYTES));
-    attr_done = true;
-  }
   const int64_t np = w.np;
   static const bool pair = getenv("BBO_TF32_SINGLE") == nullptr;    // paired row blocks by default
   static const bool clus = getenv("BBO_TF32_NO_CLUSTER") == nullptr; // 2-CTA clusters
   static const bool two_sm = getenv("BBO_TF32_NO_2SM") == nullptr;   // cta_group::2 MMA (else TMA multicast)
-  static bool attr2 = false;
-  if (pair && !attr2) {
+  static DeviceOnce attr2_once;
+  if (pair && attr2_once.first()) {
     BBO_CUDA_CHECK(cudaFuncSetAttribute(k_vnorm_tf32_pair<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         tfp::SMEM_BYTES));
     BBO_CUDA_CHECK(cudaFuncSetAttribute(k_vnorm_tf32_pair<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         tfp::SMEM_BYTES));
     BBO_CUDA_CHECK(cudaFuncSetAttribute(k_vnorm_tf32_2sm, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         tf2::SMEM_BYTES));
-    attr2 = true;
   }
   const bool use_cluster = pair && clus && (qc_pad / tf::BM) % 2 == 0;
   CUtensorMap mapA, mapB;
