@@ -974,6 +974,12 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
   const float r = x - __uint_as_float(hi);
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
 }
+// cvt.rna.tf32.f32 of a finite value with two integer-pipe instructions (round to nearest, ties away:
+// add half an ulp of the 13 dropped bits, clear them).  The conversion instruction runs on the XU pipe,
+// which the K* producers already load with one MUFU.EX2 per value.
+__device__ __forceinline__ uint32_t round_tf32_bits(float x) {
+  return (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+}
 __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -1119,7 +1125,7 @@ k_kstar_mma(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const uint32_
       m1 = fmaf(v[2], al0, fmaf(v[3], al1, m1));
       uint32_t u[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u[e]) : "f"(v[e]));
+      for (int e = 0; e < 4; ++e) u[e] = round_tf32_bits(v[e]);
       *reinterpret_cast<uint2*>(out0 + j) = make_uint2(u[0], u[1]);
       *reinterpret_cast<uint2*>(out1 + j) = make_uint2(u[2], u[3]);
     }
@@ -1148,6 +1154,17 @@ k_kstar_mma(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const uint32_
 // (the first form issued ~110 instructions per tile; ncu in profiles/).
 // ------------------------------------------------------------------------------------------
 constexpr int kMma2MaxD = 126;
+constexpr int kMma3MaxD = 46;    // third form: KS <= 6 (the B fragments of 4-8 candidate groups live in registers)
+// Measured (d = 20): third form 0.185 ms vs second form 0.205 ms per 37888 x 4096 values, but 0.243 vs 0.226
+// at n = 1024 (only 8 pipeline iterations per CTA against a fixed per-CTA set-up).  It is the default where it
+// has been measured faster: KS <= 3 (d <= 22) and np >= 2048; BBO_KSTAR_V3=1 forces it for every d <= 46.
+static bool use_kstar_v3(int d, int64_t np) {
+  static const bool v1 = getenv("BBO_KSTAR_V1") != nullptr, v2 = getenv("BBO_KSTAR_V2") != nullptr;
+  static const bool force = getenv("BBO_KSTAR_V3") != nullptr;
+  static const bool no_mma = getenv("BBO_KSTAR_NO_MMA") != nullptr;
+  if (v1 || v2 || no_mma || d > kMma3MaxD) return false;
+  return force || (d <= 22 && np >= 2048);
+}
 
 __global__ void __launch_bounds__(256)
 k_prescale_aug(const double* __restrict__ X, int64_t n, int64_t np, int d, int dk, int matern,
@@ -1302,7 +1319,7 @@ k_kstar_mma2(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const uint32
       m1 = fmaf(v[2], al.x, fmaf(v[3], al.y, m1));
       uint32_t u[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u[e]) : "f"(v[e]));
+      for (int e = 0; e < 4; ++e) u[e] = round_tf32_bits(v[e]);
       *reinterpret_cast<uint2*>(o0 + nt * 8) = make_uint2(u[0], u[1]);
       *reinterpret_cast<uint2*>(o1 + nt * 8) = make_uint2(u[2], u[3]);
     }
@@ -1316,6 +1333,247 @@ k_kstar_mma2(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const uint32
   if (t == 0) {
     mu[row0 + g] = hyp[2 * d + 1] + double(m0);
     mu[row0 + g + 8] = hyp[2 * d + 1] + double(m1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K* producer, third form (default for d <= 46): the same augmented 3xTF32 contraction with the ROLES
+// SWAPPED -- the training set is the 16-row A operand, streamed straight from L2 in fragment order
+// (k_prescale_frag lays it out so that one LDG.128 per lane is one A fragment), and the candidates are the
+// 8-column B operand, G groups of 8 candidates resident in registers for the whole kernel.
+//   * one A tile (6 LDG.128 at d = 20) feeds G*3*KS MMAs: 1 load per 12 MMAs instead of 1 LDSM per 3;
+//   * no shared-memory staging, no CTA barrier in the main loop: each of the 8 warps of a CTA walks its
+//     own interleaved share of the observation tiles (tile = 8*it + warp) with the next tile's fragments
+//     prefetched, and G independent accumulator chains per warp hide the MMA / MUFU latency;
+//   * mu = c + K* alpha: per-lane partials over the observation rows it owns, reduced over the row lanes
+//     by shuffles and over the 8 warps through shared memory in a fixed order (deterministic).
+// CTA = 8*G candidates x all observations; grid = qc_pad / (8*G).
+// Fragment layout (uint32): Afrag[((tile*KS + ks)*2 + hl)*128 + lane*4 + f], hl 0 = hi, 1 = lo,
+//   f: a0 (g, t), a1 (g+8, t), a2 (g, t+4), a3 (g+8, t+4) of the 16 x 8 slab (tile, ks).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_prescale_frag(const double* __restrict__ X, int64_t n, int64_t np, int d, int ks_n, int matern,
+                const double* __restrict__ hyp, const double* __restrict__ alpha, uint32_t* __restrict__ Afrag,
+                float* __restrict__ alpha32) {
+  // one warp per observation: the row's augmented vector, then scattered into fragment order
+  const int64_t j = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= np) return;
+  const int dk = ks_n * 8;
+  float acc = 0.f;
+  for (int k = lane; k < d; k += 32) {
+    const float v = (j < n) ? float(X[j * d + k] * hyp[d + k]) : 0.f;
+    acc = fmaf(v, v, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  const int64_t tile = j >> 4;
+  const int r = int(j & 15), g = r & 7, up = r >> 3;         // row within the tile: a0/a2 (g) or a1/a3 (g+8)
+  for (int k = lane; k < dk; k += 32) {
+    float v = 0.f;
+    if (k < d) v = (j < n) ? float(X[j * d + k] * hyp[d + k]) : 0.f;
+    else if (k == d) v = 1.f;
+    else if (k == d + 1) v = (j < n) ? (matern ? acc : -0.5f * 1.4426950408889634f * acc) : (matern ? 1e8f : -1e4f);
+    uint32_t hi, lo;
+    split_tf32(v, hi, lo);
+    const int ks = k >> 3, kc = k & 7, t = kc & 3, f = up + 2 * (kc >> 2);
+    const int64_t base = ((tile * ks_n + ks) * 2) * 128 + (g * 4 + t) * 4 + f;
+    Afrag[base] = hi;
+    Afrag[base + 128] = lo;
+  }
+  if (lane == 0) alpha32[j] = (j < n) ? float(alpha[j]) : 0.f;
+}
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(tf::smem_u32(dst)), "l"(src), "r"(bytes), "r"(tf::smem_u32(bar))
+               : "memory");
+}
+
+template <int KS>
+struct Kstar3Cfg {
+  static constexpr int kTileBytes = KS * 2 * 512;              // one 16-observation tile, hi + lo fragments
+  static constexpr int kStageBytes = 8 * kTileBytes + 512;     // 8 tiles (one per warp) + 128 alpha values
+  static constexpr int kStages = 3;
+  static constexpr size_t kSmem = size_t(kStages) * kStageBytes + 2 * kStages * sizeof(uint64_t);
+};
+
+template <typename T1, int KS, int G, bool MATERN>
+__global__ void __launch_bounds__(256, (G * KS <= 12) ? 2 : 1)
+k_kstar_mma3(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const uint32_t* __restrict__ Afrag,
+             int64_t np, const double* __restrict__ hyp, const float* __restrict__ alpha32,
+             float* __restrict__ Ks, double* __restrict__ mu) {
+  using Cfg = Kstar3Cfg<KS>;
+  extern __shared__ __align__(128) unsigned char k3_sm[];
+  __shared__ float red[8][8 * G];
+  uint64_t* full = reinterpret_cast<uint64_t*>(k3_sm + size_t(Cfg::kStages) * Cfg::kStageBytes);
+  uint64_t* empty = full + Cfg::kStages;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int d = h.d;
+  const float eps = MATERN ? float(h.pairwise_eps) : 0.f;
+  const float s2 = float(hyp[2 * d]);
+  const float kLog2e = 1.4426950408889634f;
+  const float l2s2 = __log2f(s2);
+  const int64_t cand0 = int64_t(blockIdx.x) * (8 * G);
+  const int niter = int(np / 128);                          // 8 tiles of 16 observations per iteration
+
+  // ---- TMA producer (thread 0): one bulk copy of the 8 fragment-ordered tiles + one of the alpha slice
+  // per stage, completion on the stage's "full" mbarrier; a stage is refilled once all 8 warps have
+  // arrived on its "empty" mbarrier (they do as soon as their fragments are in registers).
+  auto produce = [&](int it) {
+    const int st = it % Cfg::kStages;
+    unsigned char* dst = k3_sm + size_t(st) * Cfg::kStageBytes;
+    tf::mbar_expect_tx(&full[st], uint32_t(Cfg::kStageBytes));
+    bulk_g2s(dst, reinterpret_cast<const unsigned char*>(Afrag) + size_t(it) * 8 * Cfg::kTileBytes,
+             uint32_t(8 * Cfg::kTileBytes), &full[st]);
+    bulk_g2s(dst + 8 * Cfg::kTileBytes, alpha32 + size_t(it) * 128, 512u, &full[st]);
+  };
+  if (tid == 0) {
+    for (int st = 0; st < Cfg::kStages; ++st) {
+      tf::mbar_init(&full[st], 1);
+      tf::mbar_init(&empty[st], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (int it = 0; it < Cfg::kStages - 1 && it < niter; ++it) produce(it);
+
+  // ---- candidate vectors, built ONCE per CTA in shared memory (a per-warp build repeats ~1700 mostly
+  // FP64 instructions eight times and was 46 % of the kernel's samples), then read as B fragments:
+  // candidate cand0 + 8*grp + g, elements k = 8 ks + t (b0) and 8 ks + t + 4 (b1)
+  constexpr int DK = KS * 8, NC = 8 * G, SV = DK + 1;
+  __shared__ float sv[NC * SV];
+  __shared__ uint32_t shi[NC * SV], slo[NC * SV];
+  __shared__ float srow[NC];
+  for (int e = tid; e < NC * DK; e += 256) {
+    const int cnd = e / DK, k = e % DK;
+    float v = 0.f;
+    if (k < d) {
+      const int64_t r = cand0 + cnd;
+      const double x = (r < qc) ? double(Xq[r * d + k]) : 0.0;
+      v = float(x * hyp[d + k]) - eps;
+    }
+    sv[cnd * SV + k] = v;
+  }
+  __syncthreads();
+  if (tid < NC) {
+    float an = 0.f;
+    for (int k = 0; k < d; ++k) an = fmaf(sv[tid * SV + k], sv[tid * SV + k], an);
+    srow[tid] = MATERN ? an : fmaf(-0.5f * kLog2e, an, l2s2);
+  }
+  __syncthreads();
+  for (int e = tid; e < NC * DK; e += 256) {
+    const int cnd = e / DK, k = e % DK;
+    float u = 0.f;
+    if (k < d) u = (MATERN ? -2.f : kLog2e) * sv[cnd * SV + k];
+    else if (k == d) u = srow[cnd];
+    else if (k == d + 1) u = 1.f;
+    split_tf32(u, shi[cnd * SV + k], slo[cnd * SV + k]);
+  }
+  __syncthreads();
+  uint32_t bhi[G][KS][2], blo[G][KS][2];
+#pragma unroll
+  for (int grp = 0; grp < G; ++grp)
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int f = 0; f < 2; ++f) {
+        const int idx = (8 * grp + g) * SV + ks * 8 + t + 4 * f;
+        bhi[grp][ks][f] = shi[idx];
+        blo[grp][ks][f] = slo[idx];
+      }
+
+  float m[G][2];
+#pragma unroll
+  for (int grp = 0; grp < G; ++grp) m[grp][0] = m[grp][1] = 0.f;
+  for (int it = 0; it < niter; ++it) {
+    const int st = it % Cfg::kStages;
+    const uint32_t par = uint32_t(it / Cfg::kStages) & 1u;
+    if (tid == 0) {          // keep kStages - 1 iterations in flight: refill the stage read one iteration ago
+      const int nx = it + Cfg::kStages - 1;
+      if (nx < niter) {
+        if (nx >= Cfg::kStages) tf::mbar_wait(&empty[nx % Cfg::kStages], uint32_t(nx / Cfg::kStages - 1) & 1u);
+        produce(nx);
+      }
+    }
+    __syncwarp();
+    tf::mbar_wait(&full[st], par);
+    const unsigned char* stage = k3_sm + size_t(st) * Cfg::kStageBytes;
+    const uint4* fr = reinterpret_cast<const uint4*>(stage + warp * Cfg::kTileBytes) + lane;
+    uint4 a_cur[KS][2];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      a_cur[ks][0] = fr[(ks * 2) * 32];
+      a_cur[ks][1] = fr[(ks * 2 + 1) * 32];
+    }
+    const float* als = reinterpret_cast<const float*>(stage + 8 * Cfg::kTileBytes) + warp * 16;
+    const float al0 = als[g], al1 = als[g + 8];
+    __syncwarp();
+    if (lane == 0) tf::mbar_arrive(&empty[st]);
+    const int64_t tile = int64_t(it) * 8 + warp;
+    float* out = Ks + (cand0 + 2 * t) * np + tile * 16 + g;
+    // four candidate groups at a time: consecutive MMAs belong to four independent accumulator chains
+#pragma unroll
+    for (int g4 = 0; g4 < G; g4 += 4) {
+      float c[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const uint32_t (&ah)[4] = reinterpret_cast<const uint32_t (&)[4]>(a_cur[ks][0]);
+        const uint32_t (&alw)[4] = reinterpret_cast<const uint32_t (&)[4]>(a_cur[ks][1]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mma_tf32_16x8x8(c[j], alw, bhi[g4 + j][ks][0], bhi[g4 + j][ks][1]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mma_tf32_16x8x8(c[j], ah, blo[g4 + j][ks][0], blo[g4 + j][ks][1]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mma_tf32_16x8x8(c[j], ah, bhi[g4 + j][ks][0], bhi[g4 + j][ks][1]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int grp = g4 + j;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (!MATERN) {
+            v[e] = ex2_approx(fminf(c[j][e], l2s2));
+          } else {
+            const float r = 2.2360679775f * sqrtf(fmaxf(c[j][e], 0.f));
+            v[e] = s2 * fmaf(r, fmaf(r, 1.f / 3.f, 1.f), 1.f) * ex2_approx(-kLog2e * r);
+          }
+        }
+        // c0 (obs g, cand 2t), c1 (obs g, cand 2t+1), c2 (obs g+8, cand 2t), c3 (obs g+8, cand 2t+1)
+        m[grp][0] = fmaf(v[0], al0, fmaf(v[2], al1, m[grp][0]));
+        m[grp][1] = fmaf(v[1], al0, fmaf(v[3], al1, m[grp][1]));
+        uint32_t u[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) u[e] = round_tf32_bits(v[e]);
+        float* o = out + int64_t(8 * grp) * np;
+        reinterpret_cast<uint32_t*>(o)[0] = u[0];
+        reinterpret_cast<uint32_t*>(o + np)[0] = u[1];
+        reinterpret_cast<uint32_t*>(o)[8] = u[2];
+        reinterpret_cast<uint32_t*>(o + np)[8] = u[3];
+      }
+    }
+  }
+  // mu: sum over the observation rows (lane bits 2..4), then over the 8 warps in a fixed order
+#pragma unroll
+  for (int grp = 0; grp < G; ++grp)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      float x = m[grp][e];
+      x += __shfl_xor_sync(0xffffffffu, x, 4);
+      x += __shfl_xor_sync(0xffffffffu, x, 8);
+      x += __shfl_xor_sync(0xffffffffu, x, 16);
+      if (g == 0) red[warp][8 * grp + 2 * t + e] = x;
+    }
+  __syncthreads();
+  if (tid < 8 * G) {
+    float x = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) x += red[w][tid];
+    mu[cand0 + tid] = hyp[2 * d + 1] + double(x);
   }
 }
 
@@ -1466,7 +1724,48 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
   prof_begin(kProfKstar, st);
   static const bool use_mma = getenv("BBO_KSTAR_NO_MMA") == nullptr;
   static const bool use_v1 = getenv("BBO_KSTAR_V1") != nullptr;
-  if (use_mma && !use_v1 && s.h.d <= kMma2MaxD) {
+  static const bool use_v2 = getenv("BBO_KSTAR_V2") != nullptr;
+  if (use_kstar_v3(s.h.d, np)) {
+    const int ks = (s.h.d + 2 + 7) / 8;
+    const bool matern = s.h.kind == BBO_KERNEL_MATERN52;
+#define BBO_KSTAR_MMA3_L(T_, KS_, G_, M_)                                                                       \
+  k_kstar_mma3<T_, KS_, G_, M_><<<unsigned(qc_pad / (8 * G_)), 256, Kstar3Cfg<KS_>::kSmem, st>>>(               \
+      s.h, static_cast<const T_*>(Xq), qc, t.Xhi, np, s.hyp, t.alpha32, t.Ks[buf], t.mu[buf])
+#define BBO_KSTAR_MMA3(KS_, G_)                                                                                 \
+  case KS_: {                                                                                                   \
+    static DeviceOnce attr_once;                                                                                \
+    if (attr_once.first()) {                                                                                    \
+      const int sm = int(Kstar3Cfg<KS_>::kSmem);                                                                \
+      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_mma3<float, KS_, G_, false>,                                  \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, sm));                    \
+      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_mma3<float, KS_, G_, true>,                                   \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, sm));                    \
+      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_mma3<double, KS_, G_, false>,                                 \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, sm));                    \
+      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_mma3<double, KS_, G_, true>,                                  \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, sm));                    \
+    }                                                                                                           \
+    if (xq_is_f32) {                                                                                            \
+      if (matern) BBO_KSTAR_MMA3_L(float, KS_, G_, true);                                                       \
+      else BBO_KSTAR_MMA3_L(float, KS_, G_, false);                                                             \
+    } else {                                                                                                    \
+      if (matern) BBO_KSTAR_MMA3_L(double, KS_, G_, true);                                                      \
+      else BBO_KSTAR_MMA3_L(double, KS_, G_, false);                                                            \
+    }                                                                                                           \
+  } break;
+    switch (ks) {
+      BBO_KSTAR_MMA3(1, 8)
+      BBO_KSTAR_MMA3(2, 4)
+      BBO_KSTAR_MMA3(3, 4)
+      BBO_KSTAR_MMA3(4, 4)
+      BBO_KSTAR_MMA3(5, 4)
+      BBO_KSTAR_MMA3(6, 4)
+      default:
+        return BBO_ERR_BAD_ARG;
+    }
+#undef BBO_KSTAR_MMA3
+#undef BBO_KSTAR_MMA3_L
+  } else if (use_mma && !use_v1 && s.h.d <= kMma2MaxD) {
     const int ks = (s.h.d + 2 + 7) / 8;
     const unsigned grid = unsigned(qc_pad / 128);
     const bool matern = s.h.kind == BBO_KERNEL_MATERN52;
@@ -1675,7 +1974,14 @@ int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const vo
   const int d = s.h.d;
   static const bool use_mma = getenv("BBO_KSTAR_NO_MMA") == nullptr;
   static const bool use_v1 = getenv("BBO_KSTAR_V1") != nullptr;
-  if (use_mma && !use_v1 && d <= kMma2MaxD) {
+  static const bool use_v2 = getenv("BBO_KSTAR_V2") != nullptr;
+  if (use_kstar_v3(d, w.np)) {
+    // fragment-ordered training set: uses the Xhi and Xlo regions back to back (2 np DK words <= both)
+    k_prescale_frag<<<unsigned(ceil_div(w.np, 8)), 256, 0, st>>>(s.X, s.n, w.np, d, (d + 2 + 7) / 8,
+                                                                s.h.kind == BBO_KERNEL_MATERN52 ? 1 : 0, s.hyp, s.alpha,
+                                                                t.Xhi, t.alpha32);
+    BBO_LAUNCH_CHECK();
+  } else if (use_mma && !use_v1 && d <= kMma2MaxD) {
     const int dk = 8 * ((d + 2 + 7) / 8);
     k_prescale_aug<<<unsigned(ceil_div(w.np, 8)), 256, 0, st>>>(s.X, s.n, w.np, d, dk,
                                                                s.h.kind == BBO_KERNEL_MATERN52 ? 1 : 0, s.hyp, s.alpha,

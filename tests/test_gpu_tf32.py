@@ -18,6 +18,8 @@ TOL = 1e-3
     (1024, 20, 20000, O.RBF),       # config-2 shape, > 148 tiles (chunk of 148 x 128)
     (515, 33, 3000, O.MATERN52),    # d not a multiple of 4
     (260, 100, 2000, O.RBF),        # config-5 dimensionality
+    (2100, 20, 3000, O.RBF),        # np >= 2048, d <= 22: the register-resident-candidate K* producer (TMA staged)
+    (2060, 18, 1500, O.MATERN52),   # same producer, Matern
 ])
 def test_tf32_posterior_and_selection(n, d, q, kind, cuda_device):
     import bbo_b200 as B
