@@ -229,33 +229,12 @@ k_acq_elem(bbo_acq a, const T* __restrict__ mu, const T* __restrict__ sd, T* __r
   if (i < n) out[i] = acq_value<T>(a, mu[i], sd[i]);
 }
 
-// ------------------------------------------------------------------------------------------
-// Segment top-k: block b scans entries [b*kSeg, (b+1)*kSeg) of (score, index) and emits its k
-// best in order.  idx_in == nullptr -> index = base + position.  NaN scores and index < 0 are
-// skipped; missing slots are (-inf, -1).  256 threads.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_topk_seg(const double* __restrict__ score, const int64_t* __restrict__ idx_in, int64_t base, int64_t m,
-           int k, double* __restrict__ out_s, int64_t* __restrict__ out_i) {
-  __shared__ double ss[kSeg];
-  __shared__ int64_t si[kSeg];
-  __shared__ double ws[8];
-  __shared__ int64_t wi[8];
-  __shared__ int wp[8];
+// k selection rounds over the kSeg (score, index) pairs staged in shared memory: per round a warp-shuffle
+// arg-max with the (score desc, index asc) key, then thread 0 combines the 8 warps, emits the winner and
+// retires it.  Must be called by all 256 threads after the staging stores (it starts with a barrier).
+__device__ __forceinline__ void select_rounds(double* ss, int64_t* si, double* ws, int64_t* wi, int* wp, int k,
+                                              double* __restrict__ out_s, int64_t* __restrict__ out_i) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t s0 = int64_t(blockIdx.x) * kSeg;
-  for (int p = tid; p < kSeg; p += 256) {
-    const int64_t g = s0 + p;
-    double sc = -INFINITY;
-    int64_t ix = -1;
-    if (g < m) {
-      sc = score[g];
-      ix = idx_in ? idx_in[g] : base + g;
-      if (sc != sc) ix = -1;
-    }
-    ss[p] = sc;
-    si[p] = ix;
-  }
   __syncthreads();
   for (int r = 0; r < k; ++r) {
     double bs = -INFINITY;
@@ -297,12 +276,118 @@ k_topk_seg(const double* __restrict__ score, const int64_t* __restrict__ idx_in,
           fi = wi[w];
           fp = wp[w];
         }
-      out_s[int64_t(blockIdx.x) * k + r] = fi >= 0 ? fs : -INFINITY;
-      out_i[int64_t(blockIdx.x) * k + r] = fi;
+      out_s[r] = fi >= 0 ? fs : -INFINITY;
+      out_i[r] = fi;
       if (fp >= 0) si[fp] = -1;  // taken
     }
     __syncthreads();
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Segment top-k: block b scans entries [b*kSeg, (b+1)*kSeg) of (score, index) and emits its k
+// best in order.  idx_in == nullptr -> index = base + position.  NaN scores and index < 0 are
+// skipped; missing slots are (-inf, -1).  256 threads.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_topk_seg(const double* __restrict__ score, const int64_t* __restrict__ idx_in, int64_t base, int64_t m,
+           int k, double* __restrict__ out_s, int64_t* __restrict__ out_i) {
+  __shared__ double ss[kSeg];
+  __shared__ int64_t si[kSeg];
+  __shared__ double ws[8];
+  __shared__ int64_t wi[8];
+  __shared__ int wp[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t s0 = int64_t(blockIdx.x) * kSeg;
+  for (int p = tid; p < kSeg; p += 256) {
+    const int64_t g = s0 + p;
+    double sc = -INFINITY;
+    int64_t ix = -1;
+    if (g < m) {
+      sc = score[g];
+      ix = idx_in ? idx_in[g] : base + g;
+      if (sc != sc) ix = -1;
+    }
+    ss[p] = sc;
+    si[p] = ix;
+  }
+  select_rounds(ss, si, ws, wi, wp, k, out_s + int64_t(blockIdx.x) * k, out_i + int64_t(blockIdx.x) * k);
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused acquisition epilogue + segment top-k (the default selection path): block b turns candidates
+// [b*kSeg, (b+1)*kSeg) of a finished chunk into (variance, EI/UCB/PI score) in registers, stages the scores
+// in shared memory and emits its k best -- the scores never go through global memory unless the caller asked
+// for them.  Same arithmetic as k_acq; same ordering as k_topk_seg.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_acq_topk(bbo_gp_hyper h, bbo_acq a, int clamp_var, const double* __restrict__ hyp,
+           const double* __restrict__ mu, const double* __restrict__ vpart, int nsplit, int64_t qc_pad, int64_t qc,
+           int64_t base, int k, double* __restrict__ mu_out, double* __restrict__ var_out,
+           double* __restrict__ score_out, int32_t* __restrict__ nan_count, double* __restrict__ out_s,
+           int64_t* __restrict__ out_i) {
+  __shared__ double ss[kSeg];
+  __shared__ int64_t si[kSeg];
+  __shared__ double ws[8];
+  __shared__ int64_t wi[8];
+  __shared__ int wp[8];
+  const int tid = threadIdx.x;
+  const int64_t s0 = int64_t(blockIdx.x) * kSeg;
+  const double eps = h.kind == BBO_KERNEL_MATERN52 ? h.pairwise_eps : 0.0;
+  const double kxx = hyp[2 * h.d] * kernel_from_s(h.kind, double(h.d) * eps * eps);
+  int nans = 0;
+  for (int p = tid; p < kSeg; p += 256) {
+    const int64_t c = s0 + p;
+    double sc = -INFINITY;
+    int64_t ix = -1;
+    if (c < qc) {
+      double vn = 0.0;
+      for (int s = 0; s < nsplit; ++s) vn += vpart[int64_t(s) * qc_pad + c];
+      double var = kxx - vn + h.noise;
+      if (clamp_var) var = fmax(var, 0.0);
+      const double m = mu[c];
+      sc = acq_value<double>(a, m, sqrt(var));
+      if (mu_out) mu_out[c] = m;
+      if (var_out) var_out[c] = var;
+      if (score_out) score_out[c] = sc;
+      ix = base + c;
+      if (sc != sc) {
+        ix = -1;
+        ++nans;
+      }
+    }
+    ss[p] = sc;
+    si[p] = ix;
+  }
+  if (nans && nan_count) atomicAdd(nan_count, nans);
+  select_rounds(ss, si, ws, wi, wp, k, out_s + int64_t(blockIdx.x) * k, out_i + int64_t(blockIdx.x) * k);
+}
+
+// Merge of the per-segment lists (ma pairs) with the running top-k (k pairs, read before it is overwritten):
+// one block, ma + k <= kSeg.
+__global__ void __launch_bounds__(256)
+k_topk_merge_running(const double* __restrict__ as, const int64_t* __restrict__ ai, int ma, int k,
+                     double* __restrict__ run_s, int64_t* __restrict__ run_i) {
+  __shared__ double ss[kSeg];
+  __shared__ int64_t si[kSeg];
+  __shared__ double ws[8];
+  __shared__ int64_t wi[8];
+  __shared__ int wp[8];
+  for (int p = threadIdx.x; p < kSeg; p += 256) {
+    double sc = -INFINITY;
+    int64_t ix = -1;
+    if (p < k) {
+      sc = run_s[p];
+      ix = run_i[p];
+    } else if (p < k + ma) {
+      sc = as[p - k];
+      ix = ai[p - k];
+    }
+    if (sc != sc) ix = -1;
+    ss[p] = sc;
+    si[p] = ix;
+  }
+  select_rounds(ss, si, ws, wi, wp, k, run_s, run_i);
 }
 
 __global__ void k_topk_init(double* s, int64_t* i, int k) {
@@ -495,19 +580,31 @@ int gp_score_pool(const bbo_gp_state& s, const bbo_acq& acq, int precision, cons
   // acquisition + running top-k of one finished chunk (mu and |v|^2 partials are ready on st)
   auto consume = [&](int64_t c0, int64_t qc, const double* mu_chunk, int nsplit) -> int {
     prof_begin(kProfSelect, st);
-    k_acq<<<unsigned(ceil_div(qc, 256)), 256, 0, st>>>(
-        s.h, acq, 1, precision == BBO_PREC_TF32, s.hyp, mu_chunk, w.vpart, nsplit, w.qp, qc, w.score,
-        mu_out ? mu_out + c0 : nullptr, var_out ? var_out + c0 : nullptr, score_out ? score_out + c0 : nullptr,
-        nan_count);
-    BBO_LAUNCH_CHECK();
-    // level 1: segments of this chunk -> list A (after the k running entries)
     const int64_t nb = ceil_div(qc, kSeg);
-    BBO_CUDA_CHECK(cudaMemcpyAsync(w.la_s, topk_s, size_t(k) * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    BBO_CUDA_CHECK(cudaMemcpyAsync(w.la_i, topk_i, size_t(k) * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
-    k_topk_seg<<<unsigned(nb), 256, 0, st>>>(w.score, nullptr, index_offset + c0, qc, k, w.la_s + k, w.la_i + k);
-    BBO_LAUNCH_CHECK();
-    int rc2 = topk_levels(w.la_s, w.la_i, (nb + 1) * k, w.lb_s, w.lb_i, k, topk_s, topk_i, st);
-    if (rc2 != BBO_OK) return rc2;
+    static const bool unfused = getenv("BBO_SELECT_UNFUSED") != nullptr;
+    if (!unfused && (nb + 1) * k <= kSeg) {
+      // fused acquisition + per-segment top-k, then one merge with the running list (2 launches per chunk)
+      k_acq_topk<<<unsigned(nb), 256, 0, st>>>(
+          s.h, acq, precision == BBO_PREC_TF32, s.hyp, mu_chunk, w.vpart, nsplit, w.qp, qc, index_offset + c0, k,
+          mu_out ? mu_out + c0 : nullptr, var_out ? var_out + c0 : nullptr, score_out ? score_out + c0 : nullptr,
+          nan_count, w.la_s, w.la_i);
+      BBO_LAUNCH_CHECK();
+      k_topk_merge_running<<<1, 256, 0, st>>>(w.la_s, w.la_i, int(nb * k), k, topk_s, topk_i);
+      BBO_LAUNCH_CHECK();
+    } else {
+      k_acq<<<unsigned(ceil_div(qc, 256)), 256, 0, st>>>(
+          s.h, acq, 1, precision == BBO_PREC_TF32, s.hyp, mu_chunk, w.vpart, nsplit, w.qp, qc, w.score,
+          mu_out ? mu_out + c0 : nullptr, var_out ? var_out + c0 : nullptr, score_out ? score_out + c0 : nullptr,
+          nan_count);
+      BBO_LAUNCH_CHECK();
+      // level 1: segments of this chunk -> list A (after the k running entries)
+      BBO_CUDA_CHECK(cudaMemcpyAsync(w.la_s, topk_s, size_t(k) * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      BBO_CUDA_CHECK(cudaMemcpyAsync(w.la_i, topk_i, size_t(k) * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+      k_topk_seg<<<unsigned(nb), 256, 0, st>>>(w.score, nullptr, index_offset + c0, qc, k, w.la_s + k, w.la_i + k);
+      BBO_LAUNCH_CHECK();
+      int rc2 = topk_levels(w.la_s, w.la_i, (nb + 1) * k, w.lb_s, w.lb_i, k, topk_s, topk_i, st);
+      if (rc2 != BBO_OK) return rc2;
+    }
     prof_end(kProfSelect, st);
     return BBO_OK;
   };
