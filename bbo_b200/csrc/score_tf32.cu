@@ -1390,6 +1390,51 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
+// Candidate vectors of one chunk in B-fragment order (one warp per candidate), so that k_kstar_mma3 starts
+// with 2*KS coalesced 8-byte loads per lane instead of building the vectors per CTA:
+//   u = [log2e a', A', 1, 0..] (RBF)  |  [-2 a', |a'|^2, 1, 0..] (Matern),  a' = xq / l - eps
+//   Bfrag[((grp*KS + ks)*2 + hl)*64 + (g*4 + t)*2 + f]: candidate 8 grp + g, element 8 ks + t + 4 f.
+template <typename T1>
+__global__ void __launch_bounds__(256)
+k_prescale_cand(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, int64_t qc_pad, int ks_n,
+                const double* __restrict__ hyp, uint32_t* __restrict__ Bfrag) {
+  const int64_t c = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= qc_pad) return;
+  const int d = h.d, dk = ks_n * 8;
+  const bool matern = h.kind == BBO_KERNEL_MATERN52;
+  const float eps = matern ? float(h.pairwise_eps) : 0.f;
+  const float kLog2e = 1.4426950408889634f;
+  float an = 0.f;
+  for (int k = lane; k < d; k += 32) {
+    const double x = (c < qc) ? double(Xq[c * d + k]) : 0.0;
+    const float v = float(x * hyp[d + k]) - eps;
+    an = fmaf(v, v, an);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) an += __shfl_xor_sync(0xffffffffu, an, o);
+  const float R = matern ? an : fmaf(-0.5f * kLog2e, an, __log2f(float(hyp[2 * d])));
+  const int64_t grp = c >> 3;
+  const int g = int(c & 7);
+  for (int k = lane; k < dk; k += 32) {
+    float u = 0.f;
+    if (k < d) {
+      const double x = (c < qc) ? double(Xq[c * d + k]) : 0.0;
+      u = (matern ? -2.f : kLog2e) * (float(x * hyp[d + k]) - eps);
+    } else if (k == d) {
+      u = R;
+    } else if (k == d + 1) {
+      u = 1.f;
+    }
+    uint32_t hi, lo;
+    split_tf32(u, hi, lo);
+    const int ks = k >> 3, kc = k & 7, t = kc & 3, f = kc >> 2;
+    const int64_t base = ((grp * ks_n + ks) * 2) * 64 + (g * 4 + t) * 2 + f;
+    Bfrag[base] = hi;
+    Bfrag[base + 64] = lo;
+  }
+}
+
 template <int KS>
 struct Kstar3Cfg {
   static constexpr int kTileBytes = KS * 2 * 512;              // one 16-observation tile, hi + lo fragments
@@ -1398,9 +1443,9 @@ struct Kstar3Cfg {
   static constexpr size_t kSmem = size_t(kStages) * kStageBytes + 2 * kStages * sizeof(uint64_t);
 };
 
-template <typename T1, int KS, int G, bool MATERN>
+template <int KS, int G, bool MATERN>
 __global__ void __launch_bounds__(256, (G * KS <= 12) ? 2 : 1)
-k_kstar_mma3(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const uint32_t* __restrict__ Afrag,
+k_kstar_mma3(bbo_gp_hyper h, const uint32_t* __restrict__ Bfrag, const uint32_t* __restrict__ Afrag,
              int64_t np, const double* __restrict__ hyp, const float* __restrict__ alpha32,
              float* __restrict__ Ks, double* __restrict__ mu) {
   using Cfg = Kstar3Cfg<KS>;
@@ -1410,7 +1455,6 @@ k_kstar_mma3(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const uint32
   uint64_t* empty = full + Cfg::kStages;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int d = h.d;
-  const float eps = MATERN ? float(h.pairwise_eps) : 0.f;
   const float s2 = float(hyp[2 * d]);
   const float kLog2e = 1.4426950408889634f;
   const float l2s2 = __log2f(s2);
@@ -1439,50 +1483,23 @@ k_kstar_mma3(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const uint32
   if (tid == 0)
     for (int it = 0; it < Cfg::kStages - 1 && it < niter; ++it) produce(it);
 
-  // ---- candidate vectors, built ONCE per CTA in shared memory (a per-warp build repeats ~1700 mostly
-  // FP64 instructions eight times and was 46 % of the kernel's samples), then read as B fragments:
-  // candidate cand0 + 8*grp + g, elements k = 8 ks + t (b0) and 8 ks + t + 4 (b1)
-  constexpr int DK = KS * 8, NC = 8 * G, SV = DK + 1;
-  __shared__ float sv[NC * SV];
-  __shared__ uint32_t shi[NC * SV], slo[NC * SV];
-  __shared__ float srow[NC];
-  for (int e = tid; e < NC * DK; e += 256) {
-    const int cnd = e / DK, k = e % DK;
-    float v = 0.f;
-    if (k < d) {
-      const int64_t r = cand0 + cnd;
-      const double x = (r < qc) ? double(Xq[r * d + k]) : 0.0;
-      v = float(x * hyp[d + k]) - eps;
-    }
-    sv[cnd * SV + k] = v;
-  }
-  __syncthreads();
-  if (tid < NC) {
-    float an = 0.f;
-    for (int k = 0; k < d; ++k) an = fmaf(sv[tid * SV + k], sv[tid * SV + k], an);
-    srow[tid] = MATERN ? an : fmaf(-0.5f * kLog2e, an, l2s2);
-  }
-  __syncthreads();
-  for (int e = tid; e < NC * DK; e += 256) {
-    const int cnd = e / DK, k = e % DK;
-    float u = 0.f;
-    if (k < d) u = (MATERN ? -2.f : kLog2e) * sv[cnd * SV + k];
-    else if (k == d) u = srow[cnd];
-    else if (k == d + 1) u = 1.f;
-    split_tf32(u, shi[cnd * SV + k], slo[cnd * SV + k]);
-  }
-  __syncthreads();
+  // ---- B fragments (candidate cand0 + 8*grp + g, elements k = 8 ks + t and 8 ks + t + 4), prepared in
+  // fragment order by k_prescale_cand: 2 KS coalesced 8-byte loads per group and lane
   uint32_t bhi[G][KS][2], blo[G][KS][2];
+  {
+    const uint2* bf = reinterpret_cast<const uint2*>(Bfrag) + (int64_t(blockIdx.x) * G * KS * 2) * 32 + lane;
 #pragma unroll
-  for (int grp = 0; grp < G; ++grp)
+    for (int grp = 0; grp < G; ++grp)
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-      for (int f = 0; f < 2; ++f) {
-        const int idx = (8 * grp + g) * SV + ks * 8 + t + 4 * f;
-        bhi[grp][ks][f] = shi[idx];
-        blo[grp][ks][f] = slo[idx];
+      for (int ks = 0; ks < KS; ++ks) {
+        const uint2 hv = __ldg(bf + ((grp * KS + ks) * 2) * 32);
+        const uint2 lv = __ldg(bf + ((grp * KS + ks) * 2 + 1) * 32);
+        bhi[grp][ks][0] = hv.x;
+        bhi[grp][ks][1] = hv.y;
+        blo[grp][ks][0] = lv.x;
+        blo[grp][ks][1] = lv.y;
       }
+  }
 
   float m[G][2];
 #pragma unroll
@@ -1630,6 +1647,7 @@ struct Tf32Scratch {
   float* alpha32;
   uint32_t* Xhi;
   uint32_t* Xlo;
+  uint32_t* Bfrag;   // candidate vectors of the current chunk in B-fragment order (third K* form)
 };
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
@@ -1637,7 +1655,8 @@ size_t score_tf32_extra_bytes(int64_t n, int64_t d, int64_t qp) {
   const int64_t np = padded(n);
   return 2 * align256(size_t(qp) * np * sizeof(float)) + align256(size_t(qp) * sizeof(double)) +
          align256(size_t(np) * d * sizeof(float)) + 2 * align256(size_t(np) * sizeof(float)) +
-         2 * align256(size_t(np) * (d + 16) * sizeof(uint32_t)) + 256;
+         2 * align256(size_t(np) * (d + 16) * sizeof(uint32_t)) +
+         align256(size_t(qp) * 2 * (d + 16) * sizeof(uint32_t)) + 256;
 }
 
 static Tf32Scratch carve(const ScoreWorkspace& w, int64_t d) {
@@ -1660,6 +1679,8 @@ static Tf32Scratch carve(const ScoreWorkspace& w, int64_t d) {
   t.Xhi = reinterpret_cast<uint32_t*>(p);
   p += align256(size_t(w.np) * (d + 16) * sizeof(uint32_t));
   t.Xlo = reinterpret_cast<uint32_t*>(p);
+  p += align256(size_t(w.np) * (d + 16) * sizeof(uint32_t));
+  t.Bfrag = reinterpret_cast<uint32_t*>(p);
   return t;
 }
 
@@ -1728,30 +1749,28 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
   if (use_kstar_v3(s.h.d, np)) {
     const int ks = (s.h.d + 2 + 7) / 8;
     const bool matern = s.h.kind == BBO_KERNEL_MATERN52;
-#define BBO_KSTAR_MMA3_L(T_, KS_, G_, M_)                                                                       \
-  k_kstar_mma3<T_, KS_, G_, M_><<<unsigned(qc_pad / (8 * G_)), 256, Kstar3Cfg<KS_>::kSmem, st>>>(               \
-      s.h, static_cast<const T_*>(Xq), qc, t.Xhi, np, s.hyp, t.alpha32, t.Ks[buf], t.mu[buf])
+    if (xq_is_f32)
+      k_prescale_cand<float><<<unsigned(qc_pad / 8), 256, 0, st>>>(s.h, static_cast<const float*>(Xq), qc, qc_pad, ks,
+                                                                  s.hyp, t.Bfrag);
+    else
+      k_prescale_cand<double><<<unsigned(qc_pad / 8), 256, 0, st>>>(s.h, static_cast<const double*>(Xq), qc, qc_pad,
+                                                                   ks, s.hyp, t.Bfrag);
+    BBO_LAUNCH_CHECK();
+#define BBO_KSTAR_MMA3_L(KS_, G_, M_)                                                                           \
+  k_kstar_mma3<KS_, G_, M_><<<unsigned(qc_pad / (8 * G_)), 256, Kstar3Cfg<KS_>::kSmem, st>>>(                   \
+      s.h, t.Bfrag, t.Xhi, np, s.hyp, t.alpha32, t.Ks[buf], t.mu[buf])
 #define BBO_KSTAR_MMA3(KS_, G_)                                                                                 \
   case KS_: {                                                                                                   \
     static DeviceOnce attr_once;                                                                                \
     if (attr_once.first()) {                                                                                    \
       const int sm = int(Kstar3Cfg<KS_>::kSmem);                                                                \
-      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_mma3<float, KS_, G_, false>,                                  \
+      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_mma3<KS_, G_, false>,                                         \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, sm));                    \
-      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_mma3<float, KS_, G_, true>,                                   \
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, sm));                    \
-      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_mma3<double, KS_, G_, false>,                                 \
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, sm));                    \
-      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_mma3<double, KS_, G_, true>,                                  \
+      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_mma3<KS_, G_, true>,                                          \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, sm));                    \
     }                                                                                                           \
-    if (xq_is_f32) {                                                                                            \
-      if (matern) BBO_KSTAR_MMA3_L(float, KS_, G_, true);                                                       \
-      else BBO_KSTAR_MMA3_L(float, KS_, G_, false);                                                             \
-    } else {                                                                                                    \
-      if (matern) BBO_KSTAR_MMA3_L(double, KS_, G_, true);                                                      \
-      else BBO_KSTAR_MMA3_L(double, KS_, G_, false);                                                            \
-    }                                                                                                           \
+    if (matern) BBO_KSTAR_MMA3_L(KS_, G_, true);                                                                \
+    else BBO_KSTAR_MMA3_L(KS_, G_, false);                                                                      \
   } break;
     switch (ks) {
       BBO_KSTAR_MMA3(1, 8)
