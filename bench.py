@@ -100,6 +100,10 @@ def cpu_score_rate(a, steps, warmup):
     return a.cpu_sample / best[0], best[0], best[1]
 
 
+def emit_line(line):   # rebound by main() to the saved stdout descriptor
+    print(json.dumps(line), flush=True)
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -118,7 +122,7 @@ def run_reference(a):
         "e2e": {"value": rate, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -419,13 +423,25 @@ def run_b200(a):
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
             "fit": fit, "other_mode": other, "top1": {"score": float(top_s[0]), "index": int(top_i[0])},
         }
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
     a = parse()
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on
+    # rank 0), so everything but the result line is sent to stderr: fd 1 is pointed at fd 2 for the run and the
+    # line goes to the saved descriptor.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global emit_line
+
+    def emit_line(line):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     if a.impl == "reference":
         run_reference(a)
     else:
