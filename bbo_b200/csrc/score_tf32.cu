@@ -2016,8 +2016,12 @@ int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const vo
                                                            t.alpha32);
     BBO_LAUNCH_CHECK();
   }
-  BBO_CUDA_CHECK(cudaEventRecord(aux->entry, st));
-  BBO_CUDA_CHECK(cudaStreamWaitEvent(aux->sk, aux->entry, 0));
+  // one stream (default): stream order already is the dependency chain, no events needed
+  const bool two_streams = aux->sk != st;
+  if (two_streams) {
+    BBO_CUDA_CHECK(cudaEventRecord(aux->entry, st));
+    BBO_CUDA_CHECK(cudaStreamWaitEvent(aux->sk, aux->entry, 0));
+  }
   const int64_t nchunk = ceil_div(q, w.qp);
   auto chunk_len = [&](int64_t i) { return (q - i * w.qp < w.qp) ? q - i * w.qp : w.qp; };
   auto chunk_ptr = [&](int64_t i) { return static_cast<const char*>(Xq) + size_t(i) * w.qp * d * esz; };
@@ -2025,26 +2029,27 @@ int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const vo
     const int64_t qc = chunk_len(0);
     rc = launch_kstar(s, w, t, 0, chunk_ptr(0), xq_is_f32, qc, ceil_div(qc, 128) * 128, aux->sk);
     if (rc != BBO_OK) return rc;
-    BBO_CUDA_CHECK(cudaEventRecord(aux->kdone[0], aux->sk));
+    if (two_streams) BBO_CUDA_CHECK(cudaEventRecord(aux->kdone[0], aux->sk));
   }
   for (int64_t i = 0; i < nchunk; ++i) {
     const int buf = int(i & 1);
     if (i + 1 < nchunk) {
       const int nb = buf ^ 1;
-      if (i >= 1) BBO_CUDA_CHECK(cudaStreamWaitEvent(aux->sk, aux->pdone[nb], 0));   // chunk i-1 released buffer nb
+      if (two_streams && i >= 1)
+        BBO_CUDA_CHECK(cudaStreamWaitEvent(aux->sk, aux->pdone[nb], 0));   // chunk i-1 released buffer nb
       const int64_t qn = chunk_len(i + 1);
       rc = launch_kstar(s, w, t, nb, chunk_ptr(i + 1), xq_is_f32, qn, ceil_div(qn, 128) * 128, aux->sk);
       if (rc != BBO_OK) return rc;
-      BBO_CUDA_CHECK(cudaEventRecord(aux->kdone[nb], aux->sk));
+      if (two_streams) BBO_CUDA_CHECK(cudaEventRecord(aux->kdone[nb], aux->sk));
     }
     const int64_t qc = chunk_len(i);
-    BBO_CUDA_CHECK(cudaStreamWaitEvent(st, aux->kdone[buf], 0));
+    if (two_streams) BBO_CUDA_CHECK(cudaStreamWaitEvent(st, aux->kdone[buf], 0));
     int nsplit = 1;
     rc = launch_panel(s, w, t, buf, ceil_div(qc, 128) * 128, &nsplit, st);
     if (rc != BBO_OK) return rc;
     rc = consume(i * w.qp, qc, t.mu[buf], nsplit);
     if (rc != BBO_OK) return rc;
-    BBO_CUDA_CHECK(cudaEventRecord(aux->pdone[buf], st));
+    if (two_streams) BBO_CUDA_CHECK(cudaEventRecord(aux->pdone[buf], st));
   }
   return BBO_OK;
 }
