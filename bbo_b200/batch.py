@@ -133,14 +133,37 @@ class CudaGPBatch:
         gp.install_state(s["hyp"][b], s["linv"][b], s["alpha"][b])
         return gp
 
+    def _score_pools_batched(self, Xq: torch.Tensor, acq_factory, k: int):
+        """All problems in one set of launches (``bbo_gp_score_pool_batched``, blockIdx.z = problem)."""
+        from .acquisitions import as_descriptor
+        s = self._state
+        q = Xq.shape[1]
+        with torch.cuda.device(self._device):
+            xq = Xq.detach().to(device=self._device, dtype=_F64).contiguous()
+            arr = (_lib.Acq * self.B)(*[as_descriptor(acq_factory(b)) for b in range(self.B)])
+            acq_dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self._device)
+            out_s = torch.empty(self.B, k, dtype=_F64, device=self._device)
+            out_i = torch.empty(self.B, k, dtype=torch.int64, device=self._device)
+            nbytes = int(self._lib.bbo_gp_score_batched_workspace_bytes(self.n, self.d, self.B, q))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self._device)
+            h = self._hyper()
+            _lib.check(self._lib.bbo_gp_score_pool_batched(
+                C.byref(h), self.n, self.B, _lib.ptr(self._X), _lib.ptr(s["hyp"]), _lib.ptr(s["linv"]),
+                _lib.ptr(s["alpha"]), _lib.ptr(acq_dev), _lib.ptr(xq), q, k, _lib.ptr(out_s), _lib.ptr(out_i),
+                _lib.ptr(ws), ws.numel(), _lib.stream_ptr(self._device)), "bbo_gp_score_pool_batched")
+        return out_s, out_i
+
     def score_pools(self, Xq: torch.Tensor, acq_factory, k: int = 1, *, precision: str = "fp64", n_streams: int = 8):
         """Score one pool per problem concurrently: Xq (B,q,d); acq_factory(b) -> acquisition.
-        Problems are issued round-robin on `n_streams` CUDA streams so that the small per-problem
-        kernels overlap.  Returns (scores (B,k), indices (B,k))."""
+        FP64 mode: one batched library call for all problems (``bbo_gp_score_pool_batched``).  TF32 mode (or
+        pools too large for the single-merge selection): problems are issued round-robin on `n_streams` CUDA
+        streams so that the per-problem kernels overlap.  Returns (scores (B,k), indices (B,k))."""
         if Xq.dim() != 3 or Xq.shape[0] != self.B or Xq.shape[2] != self.d:
             raise ValueError(f"pools must be ({self.B},q,{self.d})")
         self.factorize()
         q = Xq.shape[1]
+        if precision == "fp64" and q >= 1 and (q // 2048 + 2) * k <= 2048:
+            return self._score_pools_batched(Xq, acq_factory, k)
         gps: List[CudaGP] = [self.problem(b, q_chunk=max(128, (q + 127) // 128 * 128)) for b in range(self.B)]
         streams = [torch.cuda.Stream(device=self._device) for _ in range(max(1, n_streams))]
         cur = torch.cuda.current_stream(self._device)

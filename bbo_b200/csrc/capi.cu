@@ -325,6 +325,23 @@ int bbo_gp_score_pool_host(const bbo_gp_state* st, const bbo_acq* acq, int32_t p
   return BBO_OK;
 }
 
+size_t bbo_gp_score_batched_workspace_bytes(int64_t n, int64_t d, int64_t batch, int64_t q) {
+  if (n < 1 || d < 1 || batch < 1 || q < 1) return 0;
+  return score_batched_workspace_bytes(n, d, batch, q);
+}
+int bbo_gp_score_pool_batched(const bbo_gp_hyper* h, int64_t n, int64_t batch, const double* X_dev,
+                              const double* hyp_dev, const double* linv_dev, const double* alpha_dev,
+                              const bbo_acq* acq_dev, const double* Xq_dev, int64_t q, int32_t k,
+                              double* topk_score_dev, int64_t* topk_index_dev, void* workspace_dev,
+                              size_t workspace_bytes, void* stream) {
+  if (!hyper_ok(h)) return BBO_ERR_BAD_SHAPE;
+  if (!X_dev || !hyp_dev || !linv_dev || !alpha_dev || !acq_dev || !Xq_dev || !topk_score_dev || !topk_index_dev ||
+      !workspace_dev)
+    return BBO_ERR_BAD_ARG;
+  return gp_score_pool_batched(*h, n, batch, X_dev, hyp_dev, linv_dev, alpha_dev, acq_dev, Xq_dev, q, k,
+                               topk_score_dev, topk_index_dev, workspace_dev, workspace_bytes, S(stream));
+}
+
 int bbo_topk_merge(const double* score_dev, const int64_t* index_dev, int64_t m, int32_t k,
                    double* out_score_dev, int64_t* out_index_dev, void* stream) {
   if (!score_dev || !index_dev || !out_score_dev || !out_index_dev) return BBO_ERR_BAD_ARG;

@@ -74,8 +74,17 @@ template <typename T1>
 __global__ void __launch_bounds__(256)
 k_kstar(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const double* __restrict__ X, int64_t n,
         int64_t np, const double* __restrict__ hyp, const double* __restrict__ alpha,
-        double* __restrict__ Ks, double* __restrict__ mu) {
+        double* __restrict__ Ks, double* __restrict__ mu, int64_t qp) {
   __shared__ double x1s[64 * kXS], x2s[64 * kXS], ils[kDC];
+  {   // batched launch (gridDim.z problems of one shape): every operand advances by one problem
+    const int64_t b = blockIdx.z;
+    Xq += b * qc * h.d;
+    X += b * n * h.d;
+    hyp += b * (2 * h.d + 2);
+    alpha += b * np;
+    Ks += b * qp * np;
+    mu += b * qp;
+  }
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const int64_t c0 = int64_t(blockIdx.x) * 64;
   const double eps = h.kind == BBO_KERNEL_MATERN52 ? h.pairwise_eps : 0.0;
@@ -113,6 +122,9 @@ k_vnorm(const double* __restrict__ Ks, const double* __restrict__ Linv, int64_t 
   using Cfg = Cfg128x64;
   extern __shared__ __align__(16) double smem[];
   __shared__ double red[Cfg::BM][Cfg::WARPS_N];
+  Ks += int64_t(blockIdx.z) * qc_pad * np;          // batched launch: one problem per blockIdx.z
+  Linv += int64_t(blockIdx.z) * np * np;
+  vpart += int64_t(blockIdx.z) * kMaxSplit * qc_pad;
   const int64_t c0 = int64_t(blockIdx.x) * Cfg::BM;
   const double* A = Ks + c0 * np;
   double rs[Cfg::MF];
@@ -325,13 +337,22 @@ k_acq_topk(bbo_gp_hyper h, bbo_acq a, int clamp_var, const double* __restrict__ 
            const double* __restrict__ mu, const double* __restrict__ vpart, int nsplit, int64_t qc_pad, int64_t qc,
            int64_t base, int k, double* __restrict__ mu_out, double* __restrict__ var_out,
            double* __restrict__ score_out, int32_t* __restrict__ nan_count, double* __restrict__ out_s,
-           int64_t* __restrict__ out_i) {
+           int64_t* __restrict__ out_i, const bbo_acq* __restrict__ acq_batch) {
   __shared__ double ss[kSeg];
   __shared__ int64_t si[kSeg];
   __shared__ double ws[8];
   __shared__ int64_t wi[8];
   __shared__ int wp[8];
   const int tid = threadIdx.x;
+  if (acq_batch) {   // batched launch: problem blockIdx.z has its own incumbent / parameters and slices
+    const int64_t b = blockIdx.z;
+    a = acq_batch[b];
+    hyp += b * (2 * h.d + 2);
+    mu += b * qc_pad;
+    vpart += b * kMaxSplit * qc_pad;
+    out_s += b * int64_t(gridDim.x) * k;
+    out_i += b * int64_t(gridDim.x) * k;
+  }
   const int64_t s0 = int64_t(blockIdx.x) * kSeg;
   const double eps = h.kind == BBO_KERNEL_MATERN52 ? h.pairwise_eps : 0.0;
   const double kxx = hyp[2 * h.d] * kernel_from_s(h.kind, double(h.d) * eps * eps);
@@ -368,6 +389,10 @@ k_acq_topk(bbo_gp_hyper h, bbo_acq a, int clamp_var, const double* __restrict__ 
 __global__ void __launch_bounds__(256)
 k_topk_merge_running(const double* __restrict__ as, const int64_t* __restrict__ ai, int ma, int k,
                      double* __restrict__ run_s, int64_t* __restrict__ run_i) {
+  as += int64_t(blockIdx.z) * ma;                  // batched launch: one list set per blockIdx.z
+  ai += int64_t(blockIdx.z) * ma;
+  run_s += int64_t(blockIdx.z) * k;
+  run_i += int64_t(blockIdx.z) * k;
   __shared__ double ss[kSeg];
   __shared__ int64_t si[kSeg];
   __shared__ double ws[8];
@@ -509,10 +534,10 @@ static int posterior_chunk(const bbo_gp_state& s, const ScoreWorkspace& w, int p
   prof_begin(kProfKstar, st);
   if (xq_is_f32)
     k_kstar<float><<<unsigned(qc_pad / 64), 256, 0, st>>>(s.h, static_cast<const float*>(Xq), qc, s.X, s.n, w.np,
-                                                         s.hyp, s.alpha, w.Ks, w.mu);
+                                                         s.hyp, s.alpha, w.Ks, w.mu, w.qp);
   else
     k_kstar<double><<<unsigned(qc_pad / 64), 256, 0, st>>>(s.h, static_cast<const double*>(Xq), qc, s.X, s.n,
-                                                          w.np, s.hyp, s.alpha, w.Ks, w.mu);
+                                                          w.np, s.hyp, s.alpha, w.Ks, w.mu, w.qp);
   BBO_LAUNCH_CHECK();
   prof_end(kProfKstar, st);
   prof_begin(kProfVnorm, st);
@@ -587,7 +612,7 @@ int gp_score_pool(const bbo_gp_state& s, const bbo_acq& acq, int precision, cons
       k_acq_topk<<<unsigned(nb), 256, 0, st>>>(
           s.h, acq, precision == BBO_PREC_TF32, s.hyp, mu_chunk, w.vpart, nsplit, w.qp, qc, index_offset + c0, k,
           mu_out ? mu_out + c0 : nullptr, var_out ? var_out + c0 : nullptr, score_out ? score_out + c0 : nullptr,
-          nan_count, w.la_s, w.la_i);
+          nan_count, w.la_s, w.la_i, nullptr);
       BBO_LAUNCH_CHECK();
       k_topk_merge_running<<<1, 256, 0, st>>>(w.la_s, w.la_i, int(nb * k), k, topk_s, topk_i);
       BBO_LAUNCH_CHECK();
@@ -618,6 +643,64 @@ int gp_score_pool(const bbo_gp_state& s, const bbo_acq& acq, int precision, cons
     if (rc != BBO_OK) return rc;
     rc = consume(c0, qc, w.mu, nsplit);
     if (rc != BBO_OK) return rc;
+  }
+  return BBO_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Batched FP64 scoring: B independent problems of one shape (the state of a batched bbo_gp_factorize), one
+// pool of q candidates per problem, per-problem acquisition parameters.  Same kernels as the single-problem
+// path with blockIdx.z = problem; problems are processed in groups that keep K* under ~512 MB.
+// ------------------------------------------------------------------------------------------
+static int64_t batched_group(int64_t n, int64_t B, int64_t q) {
+  const int64_t np = padded(n), qp = round_chunk(q);
+  int64_t g = (int64_t(512) << 20) / (qp * np * 8);
+  if (g < 1) g = 1;
+  if (g > B) g = B;
+  if (g > 65535) g = 65535;
+  return g;
+}
+size_t score_batched_workspace_bytes(int64_t n, int64_t d, int64_t B, int64_t q) {
+  const int64_t np = padded(n), qp = round_chunk(q), g = batched_group(n, B, q);
+  const int64_t nb = ceil_div(qp, kSeg);
+  return size_t(g) * (size_t(qp) * np + size_t(kMaxSplit) * qp + qp + 2 * size_t(nb) * BBO_TOPK_MAX) * 8 + 1024;
+}
+int gp_score_pool_batched(const bbo_gp_hyper& h, int64_t n, int64_t B, const double* X, const double* hyp,
+                          const double* linv, const double* alpha, const bbo_acq* acq_dev, const double* Xq,
+                          int64_t q, int k, double* topk_s, int64_t* topk_i, void* ws, size_t ws_bytes,
+                          cudaStream_t st) {
+  if (n < 1 || B < 1 || q < 1 || h.d < 1) return BBO_ERR_BAD_SHAPE;
+  if (k < 1 || k > BBO_TOPK_MAX) return BBO_ERR_BAD_ARG;
+  if (ws_bytes < score_batched_workspace_bytes(n, h.d, B, q)) return BBO_ERR_WORKSPACE;
+  int rc = set_smem_attrs();
+  if (rc != BBO_OK) return rc;
+  const int64_t np = padded(n), qp = round_chunk(q), g = batched_group(n, B, q);
+  const int64_t nb = ceil_div(q, kSeg);
+  if ((nb + 1) * k > kSeg) return BBO_ERR_BAD_ARG;       // pool too large for the single-merge selection
+  char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) / 256 * 256);
+  double* Ks = reinterpret_cast<double*>(p);
+  double* vpart = Ks + size_t(g) * qp * np;
+  double* mu = vpart + size_t(g) * kMaxSplit * qp;
+  double* la_s = mu + size_t(g) * qp;
+  int64_t* la_i = reinterpret_cast<int64_t*>(la_s + size_t(g) * ceil_div(qp, kSeg) * BBO_TOPK_MAX);
+  const int nsplit = 1;                                   // B problems already fill the machine
+  k_topk_init<<<unsigned(ceil_div(B * k, 256)), 256, 0, st>>>(topk_s, topk_i, int(B * k));
+  BBO_LAUNCH_CHECK();
+  for (int64_t b0 = 0; b0 < B; b0 += g) {
+    const unsigned gb = unsigned((B - b0 < g) ? B - b0 : g);
+    k_kstar<double><<<dim3(unsigned(qp / 64), 1, gb), 256, 0, st>>>(
+        h, Xq + b0 * q * h.d, q, X + b0 * n * h.d, n, np, hyp + b0 * (2 * h.d + 2), alpha + b0 * np, Ks, mu, qp);
+    BBO_LAUNCH_CHECK();
+    k_vnorm<<<dim3(unsigned(qp / 128), unsigned(nsplit), gb), Cfg128x64::THREADS, Cfg128x64::SMEM_BYTES, st>>>(
+        Ks, linv + b0 * np * np, np, qp, vpart);
+    BBO_LAUNCH_CHECK();
+    k_acq_topk<<<dim3(unsigned(nb), 1, gb), 256, 0, st>>>(h, bbo_acq{}, 0, hyp + b0 * (2 * h.d + 2), mu, vpart,
+                                                         nsplit, qp, q, 0, k, nullptr, nullptr, nullptr, nullptr,
+                                                         la_s, la_i, acq_dev + b0);
+    BBO_LAUNCH_CHECK();
+    k_topk_merge_running<<<dim3(1, 1, gb), 256, 0, st>>>(la_s, la_i, int(nb * k), k, topk_s + b0 * k,
+                                                        topk_i + b0 * k);
+    BBO_LAUNCH_CHECK();
   }
   return BBO_OK;
 }

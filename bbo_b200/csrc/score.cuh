@@ -30,6 +30,11 @@ int gp_score_pool(const bbo_gp_state& s, const bbo_acq& acq, int precision, cons
                   int64_t q, int64_t index_offset, int k, double* topk_s, int64_t* topk_i, double* mu_out,
                   double* var_out, double* score_out, int32_t* nan_count, void* ws, size_t ws_bytes,
                   int64_t q_chunk, bool keep_running, cudaStream_t st);
+size_t score_batched_workspace_bytes(int64_t n, int64_t d, int64_t B, int64_t q);
+int gp_score_pool_batched(const bbo_gp_hyper& h, int64_t n, int64_t B, const double* X, const double* hyp,
+                          const double* linv, const double* alpha, const bbo_acq* acq_dev, const double* Xq,
+                          int64_t q, int k, double* topk_s, int64_t* topk_i, void* ws, size_t ws_bytes,
+                          cudaStream_t st);
 int acq_eval(const bbo_acq& a, const void* mu, const void* sd, void* out, int64_t n, int is_f32, cudaStream_t st);
 int topk_merge(const double* score, const int64_t* index, int64_t m, int k, double* out_s, int64_t* out_i,
                cudaStream_t st);

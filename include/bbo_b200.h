@@ -21,6 +21,7 @@
  *                           and DesignerAsOptimizer.optimize's selection
  *                           (optimizers/designer_optimizer.py:29-42)
  *   bbo_gp_score_pool_host  same, candidates in HOST memory (H2D overlapped)
+ *   bbo_gp_score_pool_batched  same for B independent small problems at once (BASELINE config 4)
  *   bbo_cov_matrix          bbo/algorithms/surrogates/gp/kernel_impl.py:40-128
  *                           (KernelProtocol: rbf/matern52, vmap and cdist forms)
  *   bbo_acq_eval            bbo/algorithms/designers/bo/acquisitions.py:18-31
@@ -260,6 +261,18 @@ int bbo_gp_score_pool_host(const bbo_gp_state* st, const bbo_acq* acq, int32_t p
                            void* staging_dev, double* topk_score_dev, int64_t* topk_index_dev,
                            void* workspace_dev, size_t workspace_bytes, int64_t q_chunk,
                            void* stream);
+
+/* Batched FP64 pool scoring: `batch` independent problems of one shape (n, d) -- the layout a batched
+ * bbo_gp_factorize leaves: X (batch,n,d), hyp (batch,2d+2), linv (batch,np,np), alpha (batch,np) -- each with its
+ * own pool Xq (batch,q,d) float64 and its own acquisition parameters acq_dev[batch] (DEVICE array of bbo_acq:
+ * the incumbent best_f differs per problem).  One set of launches serves all problems (blockIdx.z = problem).
+ * Outputs topk_score (batch,k), topk_index (batch,k), indices local to each pool.  (q/2048 + 1) * k <= 2048.  */
+size_t bbo_gp_score_batched_workspace_bytes(int64_t n, int64_t d, int64_t batch, int64_t q);
+int bbo_gp_score_pool_batched(const bbo_gp_hyper* h, int64_t n, int64_t batch, const double* X_dev,
+                              const double* hyp_dev, const double* linv_dev, const double* alpha_dev,
+                              const bbo_acq* acq_dev, const double* Xq_dev, int64_t q, int32_t k,
+                              double* topk_score_dev, int64_t* topk_index_dev, void* workspace_dev,
+                              size_t workspace_bytes, void* stream);
 
 /* Merge m (score,index) pairs (e.g. the all-gathered per-GPU top-k lists) into the k best,
  * same ordering rule.  In-place safe when out != in.                                        */

@@ -54,3 +54,24 @@ def test_batched_value_grad_train_and_scoring(B, n, d, kind, cuda_device):
         np.testing.assert_allclose(got, want, rtol=1e-7, atol=1e-9)
         np.testing.assert_allclose(np_(gb.last_values[:, b]), ovals, rtol=1e-7)
     assert int(gb.info.abs().sum()) == 0
+
+
+def test_batched_scoring_many_problems_two_groups(cuda_device):
+    """300 problems (two launch groups), pools spanning two top-k segments, per-problem incumbents: the batched
+    library call against the per-problem path and the oracle."""
+    import bbo_b200 as B200
+    from bbo_b200.batch import CudaGPBatch
+    B, n, d, q, k = 300, 64, 3, 2100, 16
+    ps, X, y, theta = _batch(B, n, d, O.RBF, 900)
+    gb = CudaGPBatch(torch.as_tensor(X), torch.as_tensor(y)[..., None], "rbf_vmap", theta=torch.as_tensor(theta),
+                     noise_variance=1e-4)
+    Xq = np.random.default_rng(2).random((B, q, d))
+    best = [float(y[b].max()) - 0.1 * (b % 3) for b in range(B)]
+    s, i = gb.score_pools(torch.as_tensor(Xq), lambda b: B200.EI(best[b]), k)
+    assert s.shape == (B, k) and i.shape == (B, k)
+    for b in (0, 1, 150, 239, 240, 299):                      # both sides of the group boundary
+        oi, os_, *_ = O.score_pool(ps[b], X[b], y[b], Xq[b], "ei", best[b], k=k)
+        np.testing.assert_array_equal(np_(i[b]), oi)
+        np.testing.assert_allclose(np_(s[b]), os_, rtol=1e-6, atol=1e-12)
+        s1, i1 = gb.problem(b).score_pool(torch.as_tensor(Xq[b]).cuda(), B200.EI(best[b]), k)
+        assert torch.equal(i1, i[b]) and torch.equal(s1, s[b])
