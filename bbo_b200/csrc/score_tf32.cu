@@ -134,6 +134,29 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// split form: issue the load, wait later (the wait names the registers so that no use can be scheduled above it)
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
+                 "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]),
+                 "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]),
+                 "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
 }  // namespace tf
 
 // ------------------------------------------------------------------------------------------
@@ -1594,6 +1617,335 @@ k_kstar_mma3(bbo_gp_hyper h, const uint32_t* __restrict__ Bfrag, const uint32_t*
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// K* producer, fourth form (default for d <= 30): the augmented 3xTF32 contraction of the second form on
+// the tcgen05 tensor cores.  The three partial products are ONE contraction of length 3 dk over
+// concatenated operand rows,
+//     candidates   Aop[c] = [ hi(u) | hi(u) | lo(u) | 0.. ]      u as in k_prescale_cand
+//     observations Bop[j] = [ hi(b) | lo(b) | hi(b) | 0.. ]      b as in k_prescale_aug
+// so Aop[c] . Bop[j] = u_hi b_hi + u_hi b_lo + u_lo b_hi is the finished exponent (RBF) / squared distance
+// (Matern).  Persistent CTAs (one per SM), 320 threads, warp specialised:
+//   warp 0    TMA producer: the 128-candidate A tile once per tile, 128-observation B tiles in a 2-stage ring
+//             (SWIZZLE_128B boxes of 128 rows x 32 words)
+//   warp 1    one thread issues tcgen05.mma kind::tf32, M = 128 x N = 128 x K = 8, 3 dk / 8 instructions per
+//             128 x 128 block; four 128-column TMEM accumulators in a ring, so the tensor core runs up to four
+//             blocks ahead of the epilogue
+//   warps 2-9 epilogue: tcgen05.ld 32 lanes x 32 columns -> ex2 (Matern: sqrt, cubic, ex2) -> mu += K* alpha ->
+//             round to TF32 (integer pipe) -> st.shared.v4 into a 128-byte-swizzled 32 x 32 staging tile ->
+//             TMA tensor store (cp.async.bulk.tensor ... bulk_group), two staging tiles per warp
+// so every K* byte leaves the SM as part of a full 128-byte line (the mma.sync forms scatter 8-byte stores)
+// and the kernel is bounded by the HBM write of the K* chunk.  mu = c + sum of the two column halves in a
+// fixed order (deterministic).
+// ------------------------------------------------------------------------------------------
+namespace ku {
+constexpr int BM = 128, BN = 128, BOXK = 32;
+constexpr int BOX_BYTES = 128 * BOXK * 4;          // 16 KB: 128 rows x 128 bytes
+constexpr int MAXBOX = 3;                          // 3 dk <= 96, dk <= 32
+constexpr int BSTAGES = 2, ACCS = 4;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 64 + 32 * EPI_WARPS;       // 320
+constexpr int OUT_BYTES = 32 * 128;                // staging tile: 32 candidates x 32 values
+constexpr int kMaxD = 30;
+static size_t smem_bytes(int nbox) {
+  return size_t(nbox) * BOX_BYTES * (1 + BSTAGES) + size_t(EPI_WARPS) * 2 * OUT_BYTES + 1024;
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t saddr, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(saddr), "r"(c0), "r"(c1)
+               : "memory");
+}
+}  // namespace ku
+
+// rows of Bop: [hi | lo | hi | 0..] of the augmented observation vector (see k_prescale_aug), ktp words per row
+__global__ void __launch_bounds__(256)
+k_prescale_aug_umma(const double* __restrict__ X, int64_t n, int64_t np, int d, int dk, int ktp, int matern,
+                    const double* __restrict__ hyp, const double* __restrict__ alpha, uint32_t* __restrict__ Bop,
+                    float* __restrict__ alpha32) {
+  const int64_t j = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= np) return;
+  float acc = 0.f;
+  for (int k = lane; k < d; k += 32) {
+    const float v = (j < n) ? float(X[j * d + k] * hyp[d + k]) : 0.f;
+    acc = fmaf(v, v, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  uint32_t* row = Bop + j * ktp;
+  for (int k = lane; k < dk; k += 32) {
+    float v = 0.f;
+    if (k < d) v = (j < n) ? float(X[j * d + k] * hyp[d + k]) : 0.f;
+    else if (k == d) v = 1.f;
+    else if (k == d + 1) v = (j < n) ? (matern ? acc : -0.5f * 1.4426950408889634f * acc) : (matern ? 1e8f : -1e4f);
+    uint32_t hi, lo;
+    split_tf32(v, hi, lo);
+    row[k] = hi;
+    row[dk + k] = lo;
+    row[2 * dk + k] = hi;
+  }
+  for (int k = 3 * dk + lane; k < ktp; k += 32) row[k] = 0u;
+  if (lane == 0) alpha32[j] = (j < n) ? float(alpha[j]) : 0.f;
+}
+
+// rows of Aop: [hi | hi | lo | 0..] of the augmented candidate vector (see k_prescale_cand)
+template <typename T1>
+__global__ void __launch_bounds__(256)
+k_prescale_cand_umma(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, int64_t qc_pad, int dk, int ktp,
+                     const double* __restrict__ hyp, uint32_t* __restrict__ Aop) {
+  const int64_t c = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= qc_pad) return;
+  const int d = h.d;
+  const bool matern = h.kind == BBO_KERNEL_MATERN52;
+  const float eps = matern ? float(h.pairwise_eps) : 0.f;
+  const float kLog2e = 1.4426950408889634f;
+  float an = 0.f;
+  for (int k = lane; k < d; k += 32) {
+    const double x = (c < qc) ? double(Xq[c * d + k]) : 0.0;
+    const float v = float(x * hyp[d + k]) - eps;
+    an = fmaf(v, v, an);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) an += __shfl_xor_sync(0xffffffffu, an, o);
+  const float R = matern ? an : fmaf(-0.5f * kLog2e, an, __log2f(float(hyp[2 * d])));
+  uint32_t* row = Aop + c * ktp;
+  for (int k = lane; k < dk; k += 32) {
+    float u = 0.f;
+    if (k < d) {
+      const double x = (c < qc) ? double(Xq[c * d + k]) : 0.0;
+      u = (matern ? -2.f : kLog2e) * (float(x * hyp[d + k]) - eps);
+    } else if (k == d) {
+      u = R;
+    } else if (k == d + 1) {
+      u = 1.f;
+    }
+    uint32_t hi, lo;
+    split_tf32(u, hi, lo);
+    row[k] = hi;
+    row[dk + k] = hi;
+    row[2 * dk + k] = lo;
+  }
+  for (int k = 3 * dk + lane; k < ktp; k += 32) row[k] = 0u;
+}
+
+template <bool MATERN>
+__global__ void __launch_bounds__(ku::THREADS, 1)
+k_kstar_umma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+             const __grid_constant__ CUtensorMap mapO, int np, int tiles, int nbox, int ksteps, int d,
+             const double* __restrict__ hyp, const float* __restrict__ alpha32, double* __restrict__ mu) {
+  using namespace tf;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full, a_empty, b_full[ku::BSTAGES], b_empty[ku::BSTAGES], t_full[ku::ACCS],
+      t_empty[ku::ACCS];
+  __shared__ uint32_t tmem_base_sh;
+  __shared__ float mu_sh[2][ku::BM];
+  __shared__ __align__(16) float al_sh[ku::EPI_WARPS][2][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  const int op_bytes = nbox * ku::BOX_BYTES;       // one operand tile (A, or one B stage)
+  const int nblk = np / ku::BN;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&a_full, 1);
+    mbar_init(&a_empty, 1);
+    for (int s = 0; s < ku::BSTAGES; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int a = 0; a < ku::ACCS; ++a) {
+      mbar_init(&t_full[a], 1);
+      mbar_init(&t_empty[a], ku::EPI_WARPS * 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_sh;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ===== TMA producer =====
+      uint32_t a_phase = 0, phase = 0;
+      int stage = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        mbar_wait(&a_empty, a_phase ^ 1);            // every MMA of the previous tile has read A
+        mbar_expect_tx(&a_full, uint32_t(op_bytes));
+        for (int b = 0; b < nbox; ++b)
+          tma_load_2d(sgen + b * ku::BOX_BYTES, &mapA, &a_full, b * ku::BOXK, tile * ku::BM);
+        a_phase ^= 1;
+        for (int nb = 0; nb < nblk; ++nb) {
+          mbar_wait(&b_empty[stage], phase ^ 1);
+          uint8_t* sb = sgen + (1 + stage) * op_bytes;
+          mbar_expect_tx(&b_full[stage], uint32_t(op_bytes));
+          for (int b = 0; b < nbox; ++b)
+            tma_load_2d(sb + b * ku::BOX_BYTES, &mapB, &b_full[stage], b * ku::BOXK, nb * ku::BN);
+          if (++stage == ku::BSTAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {   // ===== MMA issuer =====
+      // D=f32, A=B=tf32, both K-major, N=128, M=128
+      const uint32_t idesc =
+          (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(ku::BN >> 3) << 17) | (uint32_t(ku::BM >> 4) << 24);
+      uint32_t a_phase = 0, phase = 0, acc_phase = 0;
+      int stage = 0, acc = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        mbar_wait(&a_full, a_phase);
+        a_phase ^= 1;
+        for (int nb = 0; nb < nblk; ++nb) {
+          mbar_wait(&t_empty[acc], acc_phase ^ 1);
+          mbar_wait(&b_full[stage], phase);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + uint32_t(acc * ku::BN);
+          const uint32_t sb = sbase + uint32_t((1 + stage) * op_bytes);
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint32_t off = uint32_t((ks >> 2) * ku::BOX_BYTES);
+            const uint64_t adv = uint64_t((ks & 3) * 2);   // 32 bytes inside the 128-byte swizzle atom
+            tc_mma_tf32(d_tmem, make_desc(sbase + off) + adv, make_desc(sb + off) + adv, idesc, ks != 0 ? 1u : 0u);
+          }
+          tc_commit(&b_empty[stage]);
+          tc_commit(&t_full[acc]);
+          if (++stage == ku::BSTAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+          if (++acc == ku::ACCS) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
+        }
+        tc_commit(&a_empty);
+      }
+    }
+  } else {   // ===== epilogue (warps 2..9) =====
+    const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t stg = sbase + uint32_t(3 * op_bytes + ew * 2 * ku::OUT_BYTES);
+    const float s2 = float(hyp[2 * d]);
+    const float l2s2 = __log2f(s2);
+    const float kLog2e = 1.4426950408889634f;
+    const double cmean = hyp[2 * d + 1];
+    const uint32_t tlane = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(half * 64);
+    const float* abase = alpha32 + half * 64;
+    float m = 0.f;
+    // alpha of this warp's 64 columns, one block ahead (cp.async, per-warp double buffer): the values are used
+    // once per tile, so they always come from L2 and a register prefetch of one slab does not cover the latency
+    float* alw = &al_sh[ew][0][0];
+    auto alpha_fetch = [&](int nb_, int buf_) {
+      if (lane < 16) {
+        const unsigned sa = smem_u32(alw + buf_ * 64 + lane * 4);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(abase + nb_ * ku::BN + lane * 4)
+                     : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // one 32 x 32 slab: values -> K*, mu partial, TF32 bits into the swizzled staging tile, TMA store
+    auto emit = [&](const uint32_t (&r)[32], const float* al, int sbuf, int col, int crow) {
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      __syncwarp();
+      const uint32_t sdst = stg + uint32_t(sbuf * ku::OUT_BYTES + lane * 128);
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        uint32_t u[4];
+        const float4 av = *reinterpret_cast<const float4*>(al + c4 * 4);
+        const float a4[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float x = __uint_as_float(r[c4 * 4 + e]);
+          float val;
+          if (!MATERN) {
+            val = ex2_approx(fminf(x, l2s2));
+          } else {
+            const float rr = 2.2360679775f * sqrtf(fmaxf(x, 0.f));
+            val = s2 * fmaf(rr, fmaf(rr, 1.f / 3.f, 1.f), 1.f) * ex2_approx(-kLog2e * rr);
+          }
+          m = fmaf(val, a4[e], m);
+          u[e] = round_tf32_bits(val);
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdst + uint32_t((c4 ^ (lane & 7)) * 16)),
+                     "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3])
+                     : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        ku::tma_store_2d(&mapO, stg + uint32_t(sbuf * ku::OUT_BYTES), col, crow);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    };
+    // Software pipeline: while slab g is processed, the TMEM load and the alpha loads of slab g+1 are in flight.
+    // Slabs alternate between the register sets (r0, al0) = columns [0,32) and (r1, al1) = columns [32,64) of
+    // this warp's half of the 128-column accumulator.
+    uint32_t r0[32], r1[32];
+    const int my_tiles = (tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+    const int nblocks = my_tiles * nblk;     // 128 x 128 blocks this CTA produces, accumulators in ring order
+    uint32_t acc_phase = 0;
+    int acc = 0;
+    if (nblocks > 0) {
+      alpha_fetch(0, 0);
+      mbar_wait(&t_full[0], 0);
+      tc_fence_after();
+      tmem_ld32_issue(tlane, r0);
+    }
+    int tile = blockIdx.x, nb = 0, tcount = 0;
+    for (int blk = 0; blk < nblocks; ++blk) {
+      const int crow = tile * ku::BM + quarter * 32, col = nb * ku::BN + half * 64;
+      const int nb_next = (nb + 1 == nblk) ? 0 : nb + 1;
+      const float* al = alw + (blk & 1) * 64;
+      alpha_fetch(nb_next, (blk + 1) & 1);                       // next block's alpha (harmless after the last)
+      asm volatile("cp.async.wait_group 1;" ::: "memory");      // this block's alpha has landed
+      __syncwarp();
+      tmem_ld_wait(r0);
+      tmem_ld32_issue(tlane + uint32_t(acc * ku::BN + 32), r1);
+      emit(r0, al, 0, col, crow);
+      tmem_ld_wait(r1);
+      tc_fence_before();
+      mbar_arrive(&t_empty[acc]);            // both slabs of this accumulator are in registers
+      if (++acc == ku::ACCS) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+      if (blk + 1 < nblocks) {
+        mbar_wait(&t_full[acc], acc_phase);
+        tc_fence_after();
+        tmem_ld32_issue(tlane + uint32_t(acc * ku::BN), r0);
+      }
+      emit(r1, al + 32, 1, col + 32, crow);
+      __syncwarp();                          // all lanes are done with al before the buffer is refilled
+      if (nb_next == 0) {
+        // mu = c + (columns of half 0) + (columns of half 1), fixed order
+        if (half == 1) mu_sh[tcount & 1][row] = m;
+        asm volatile("bar.sync 1, %0;" ::"n"(ku::EPI_WARPS * 32) : "memory");
+        if (half == 0) mu[int64_t(tile) * ku::BM + row] = cmean + double(m + mu_sh[tcount & 1][row]);
+        m = 0.f;
+        tile += gridDim.x;
+        ++tcount;
+      }
+      nb = nb_next;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 template <int KS>
 static size_t kstar_mma2_smem() {
   constexpr int DK = KS * 8, LS = 4 * ((DK / 4 + 1) | 1);
@@ -1648,6 +2000,8 @@ struct Tf32Scratch {
   uint32_t* Xhi;
   uint32_t* Xlo;
   uint32_t* Bfrag;   // candidate vectors of the current chunk in B-fragment order (third K* form)
+  uint32_t* Aop;     // (qp, 96) candidate operand rows of the current chunk (fourth K* form, tcgen05)
+  uint32_t* Bop;     // (np, 96) observation operand rows
 };
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
@@ -1656,7 +2010,9 @@ size_t score_tf32_extra_bytes(int64_t n, int64_t d, int64_t qp) {
   return 2 * align256(size_t(qp) * np * sizeof(float)) + align256(size_t(qp) * sizeof(double)) +
          align256(size_t(np) * d * sizeof(float)) + 2 * align256(size_t(np) * sizeof(float)) +
          2 * align256(size_t(np) * (d + 16) * sizeof(uint32_t)) +
-         align256(size_t(qp) * 2 * (d + 16) * sizeof(uint32_t)) + 256;
+         align256(size_t(qp) * 2 * (d + 16) * sizeof(uint32_t)) +
+         align256(size_t(qp) * 32 * ku::MAXBOX * sizeof(uint32_t)) +
+         align256(size_t(np) * 32 * ku::MAXBOX * sizeof(uint32_t)) + 256;
 }
 
 static Tf32Scratch carve(const ScoreWorkspace& w, int64_t d) {
@@ -1681,6 +2037,10 @@ static Tf32Scratch carve(const ScoreWorkspace& w, int64_t d) {
   t.Xlo = reinterpret_cast<uint32_t*>(p);
   p += align256(size_t(w.np) * (d + 16) * sizeof(uint32_t));
   t.Bfrag = reinterpret_cast<uint32_t*>(p);
+  p += align256(size_t(w.qp) * 2 * (d + 16) * sizeof(uint32_t));
+  t.Aop = reinterpret_cast<uint32_t*>(p);
+  p += align256(size_t(w.qp) * 32 * ku::MAXBOX * sizeof(uint32_t));
+  t.Bop = reinterpret_cast<uint32_t*>(p);
   return t;
 }
 
@@ -1739,6 +2099,23 @@ static int get_aux(Tf32Aux** out) {
   return BBO_OK;
 }
 
+// fourth K* form (tcgen05): default for d <= 30; BBO_KSTAR_NO_UMMA=1 or any of the BBO_KSTAR_V1/V2/V3 /
+// BBO_KSTAR_NO_MMA switches fall back to the mma.sync / CUDA-core forms
+static bool use_kstar_umma(int d) {
+  static const bool off = getenv("BBO_KSTAR_NO_UMMA") != nullptr || getenv("BBO_KSTAR_V1") != nullptr ||
+                          getenv("BBO_KSTAR_V2") != nullptr || getenv("BBO_KSTAR_V3") != nullptr ||
+                          getenv("BBO_KSTAR_NO_MMA") != nullptr;
+  return !off && d <= ku::kMaxD;
+}
+static int sm_count() {
+  static int sms[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (sms[dev] == 0 && cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    sms[dev] = 148;
+  return sms[dev];
+}
+
 static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf32Scratch& t, int buf,
                         const void* Xq, int xq_is_f32, int64_t qc, int64_t qc_pad, cudaStream_t st) {
   const int64_t np = w.np;
@@ -1746,7 +2123,41 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
   static const bool use_mma = getenv("BBO_KSTAR_NO_MMA") == nullptr;
   static const bool use_v1 = getenv("BBO_KSTAR_V1") != nullptr;
   static const bool use_v2 = getenv("BBO_KSTAR_V2") != nullptr;
-  if (use_kstar_v3(s.h.d, np)) {
+  if (use_kstar_umma(s.h.d)) {
+    const int dk = 8 * ((s.h.d + 2 + 7) / 8), ktp = 32 * ((3 * dk + 31) / 32), nbox = ktp / 32;
+    const bool matern = s.h.kind == BBO_KERNEL_MATERN52;
+    if (xq_is_f32)
+      k_prescale_cand_umma<float><<<unsigned(qc_pad / 8), 256, 0, st>>>(s.h, static_cast<const float*>(Xq), qc, qc_pad,
+                                                                       dk, ktp, s.hyp, t.Aop);
+    else
+      k_prescale_cand_umma<double><<<unsigned(qc_pad / 8), 256, 0, st>>>(s.h, static_cast<const double*>(Xq), qc,
+                                                                        qc_pad, dk, ktp, s.hyp, t.Aop);
+    BBO_LAUNCH_CHECK();
+    static DeviceOnce attr_once;
+    if (attr_once.first()) {
+      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          int(ku::smem_bytes(ku::MAXBOX))));
+      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          int(ku::smem_bytes(ku::MAXBOX))));
+    }
+    CUtensorMap mapA, mapB, mapO;
+    int rc = make_map(&mapA, reinterpret_cast<const float*>(t.Aop), qc_pad, ktp, ku::BM, ku::BOXK);
+    if (rc != BBO_OK) return rc;
+    rc = make_map(&mapB, reinterpret_cast<const float*>(t.Bop), np, ktp, ku::BN, ku::BOXK);
+    if (rc != BBO_OK) return rc;
+    rc = make_map(&mapO, t.Ks[buf], qc_pad, np, 32, ku::BOXK);
+    if (rc != BBO_OK) return rc;
+    const int tiles = int(qc_pad / ku::BM);
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    const size_t sm = ku::smem_bytes(nbox);
+    const double* hyp = s.hyp;
+    if (matern)
+      k_kstar_umma<true><<<unsigned(grid), ku::THREADS, sm, st>>>(mapA, mapB, mapO, int(np), tiles, nbox, 3 * dk / 8,
+                                                                 s.h.d, hyp, t.alpha32, t.mu[buf]);
+    else
+      k_kstar_umma<false><<<unsigned(grid), ku::THREADS, sm, st>>>(mapA, mapB, mapO, int(np), tiles, nbox, 3 * dk / 8,
+                                                                  s.h.d, hyp, t.alpha32, t.mu[buf]);
+  } else if (use_kstar_v3(s.h.d, np)) {
     const int ks = (s.h.d + 2 + 7) / 8;
     const bool matern = s.h.kind == BBO_KERNEL_MATERN52;
     if (xq_is_f32)
@@ -1994,7 +2405,13 @@ int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const vo
   static const bool use_mma = getenv("BBO_KSTAR_NO_MMA") == nullptr;
   static const bool use_v1 = getenv("BBO_KSTAR_V1") != nullptr;
   static const bool use_v2 = getenv("BBO_KSTAR_V2") != nullptr;
-  if (use_kstar_v3(d, w.np)) {
+  if (use_kstar_umma(d)) {
+    const int dk = 8 * ((d + 2 + 7) / 8), ktp = 32 * ((3 * dk + 31) / 32);
+    k_prescale_aug_umma<<<unsigned(ceil_div(w.np, 8)), 256, 0, st>>>(s.X, s.n, w.np, d, dk, ktp,
+                                                                    s.h.kind == BBO_KERNEL_MATERN52 ? 1 : 0, s.hyp,
+                                                                    s.alpha, t.Bop, t.alpha32);
+    BBO_LAUNCH_CHECK();
+  } else if (use_kstar_v3(d, w.np)) {
     // fragment-ordered training set: uses the Xhi and Xlo regions back to back (2 np DK words <= both)
     k_prescale_frag<<<unsigned(ceil_div(w.np, 8)), 256, 0, st>>>(s.X, s.n, w.np, d, (d + 2 + 7) / 8,
                                                                 s.h.kind == BBO_KERNEL_MATERN52 ? 1 : 0, s.hyp, s.alpha,

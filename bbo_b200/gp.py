@@ -19,6 +19,8 @@ from __future__ import annotations
 import ctypes as C
 from typing import Optional, Tuple
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -39,6 +41,9 @@ def _check_2d(name: str, value):
         raise TypeError(f"Expected Tensor, got {type(value)}")
     if value.dim() != 2:
         raise ValueError(f"Expected 2D Tensor, got {value.dim()}D Tensor")
+
+
+_KS_BUDGET_MB = int(os.environ.get("BBO_TF32_KS_BUDGET_MB", "768"))   # K* bytes per TF32 chunk
 
 
 def default_q_chunk(n: int, budget_bytes: int = 512 << 20) -> int:
@@ -407,7 +412,7 @@ class CudaGP(Surrogate):
             qc = min(self._q_chunk, max(128, (q + 127) // 128 * 128))
             if prec == _lib.PREC_TF32 and q >= 148 * 128 and self._q_chunk_auto:
                 # one 128-candidate tile per SM and per wave: chunks of 148 x 128 candidates
-                qc = min(q // (148 * 128), max(1, (768 << 20) // (148 * 128 * self.np * 4))) * 148 * 128
+                qc = min(q // (148 * 128), max(1, (_KS_BUDGET_MB << 20) // (148 * 128 * self.np * 4))) * 148 * 128
             ws = self._workspace("score%d" % prec,
                                  int(self._lib.bbo_gp_score_workspace_bytes(self.n, self.d, qc, prec)))
             if running is not None:
