@@ -1624,30 +1624,34 @@ k_kstar_mma3(bbo_gp_hyper h, const uint32_t* __restrict__ Bfrag, const uint32_t*
 //     candidates   Aop[c] = [ hi(u) | hi(u) | lo(u) | 0.. ]      u as in k_prescale_cand
 //     observations Bop[j] = [ hi(b) | lo(b) | hi(b) | 0.. ]      b as in k_prescale_aug
 // so Aop[c] . Bop[j] = u_hi b_hi + u_hi b_lo + u_lo b_hi is the finished exponent (RBF) / squared distance
-// (Matern).  Persistent CTAs (one per SM), 320 threads, warp specialised:
-//   warp 0    TMA producer: the 128-candidate A tile once per tile, 128-observation B tiles in a 2-stage ring
-//             (SWIZZLE_128B boxes of 128 rows x 32 words)
-//   warp 1    one thread issues tcgen05.mma kind::tf32, M = 128 x N = 128 x K = 8, 3 dk / 8 instructions per
-//             128 x 128 block; four 128-column TMEM accumulators in a ring, so the tensor core runs up to four
-//             blocks ahead of the epilogue
-//   warps 2-9 epilogue: tcgen05.ld 32 lanes x 32 columns -> ex2 (Matern: sqrt, cubic, ex2) -> mu += K* alpha ->
-//             round to TF32 (integer pipe) -> st.shared.v4 into a 128-byte-swizzled 32 x 32 staging tile ->
-//             TMA tensor store (cp.async.bulk.tensor ... bulk_group), two staging tiles per warp
+// (Matern).  Persistent CTAs (one per SM), 576 threads, warp specialised:
+//   warp 0     TMA producer: the 128-candidate A tile once per tile, 128-observation B tiles in a 2-stage ring
+//              (SWIZZLE_128B boxes of 128 rows x 32 words)
+//   warp 1     one thread issues tcgen05.mma kind::tf32, M = 128 x N = 128 x K = 8, 3 dk / 8 instructions per
+//              128 x 128 block; four 128-column TMEM accumulators in a ring, so the tensor core runs up to four
+//              blocks ahead of the epilogue
+//   warps 2-17 epilogue, one (TMEM lane quarter, 32-column slab) per warp: tcgen05.ld 32 lanes x 32 columns ->
+//              ex2 (Matern: sqrt, cubic, ex2) -> mu += K* alpha (alpha staged one block ahead by cp.async) ->
+//              round to TF32 (integer pipe) -> st.shared.v4 into a 128-byte-swizzled 32 x 32 staging tile ->
+//              TMA tensor store (cp.async.bulk.tensor ... bulk_group)
 // so every K* byte leaves the SM as part of a full 128-byte line (the mma.sync forms scatter 8-byte stores)
-// and the kernel is bounded by the HBM write of the K* chunk.  mu = c + sum of the two column halves in a
-// fixed order (deterministic).
+// and the kernel runs at the HBM write rate of the K* chunk (4.6 TB/s under ncu; the remaining stalls are the
+// TMA store queue and the accumulator hand-over).  mu = c + the four slab partials in a fixed order
+// (deterministic).  Measured alternatives, same launch: 8 epilogue warps with a register software pipeline
+// (TMEM load of slab g+1 under the arithmetic of slab g) 130 us, the same with the B tiles TMA-multicast over a
+// 2-CTA cluster 131 us, this form 122 us, third mma.sync form 166 us.
 // ------------------------------------------------------------------------------------------
 namespace ku {
 constexpr int BM = 128, BN = 128, BOXK = 32;
 constexpr int BOX_BYTES = 128 * BOXK * 4;          // 16 KB: 128 rows x 128 bytes
 constexpr int MAXBOX = 3;                          // 3 dk <= 96, dk <= 32
 constexpr int BSTAGES = 2, ACCS = 4;
-constexpr int EPI_WARPS = 8;
-constexpr int THREADS = 64 + 32 * EPI_WARPS;       // 320
+constexpr int EPI_WARPS = 16;
+constexpr int THREADS = 64 + 32 * EPI_WARPS;       // 576
 constexpr int OUT_BYTES = 32 * 128;                // staging tile: 32 candidates x 32 values
 constexpr int kMaxD = 30;
 static size_t smem_bytes(int nbox) {
-  return size_t(nbox) * BOX_BYTES * (1 + BSTAGES) + size_t(EPI_WARPS) * 2 * OUT_BYTES + 1024;
+  return size_t(nbox) * BOX_BYTES * (1 + BSTAGES) + size_t(EPI_WARPS) * OUT_BYTES + 1024;
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t saddr, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -1738,8 +1742,8 @@ k_kstar_umma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   __shared__ __align__(8) uint64_t a_full, a_empty, b_full[ku::BSTAGES], b_empty[ku::BSTAGES], t_full[ku::ACCS],
       t_empty[ku::ACCS];
   __shared__ uint32_t tmem_base_sh;
-  __shared__ float mu_sh[2][ku::BM];
-  __shared__ __align__(16) float al_sh[ku::EPI_WARPS][2][64];
+  __shared__ float mu_sh[2][3][ku::BM];
+  __shared__ __align__(16) float al_sh[ku::EPI_WARPS][2][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -1828,33 +1832,56 @@ k_kstar_umma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         tc_commit(&a_empty);
       }
     }
-  } else {   // ===== epilogue (warps 2..9) =====
-    const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
+  } else {   // ===== epilogue (warps 2..17) =====
+    // warp = (TMEM lane quarter, 32-column slab): 16 warps, four per scheduler, so that one warp's TMEM load, MUFU
+    // and TMA-store latencies are covered by the other three
+    const int ew = warp - 2, quarter = warp & 3, colq = ew >> 2;
     const int row = quarter * 32 + lane;
-    const uint32_t stg = sbase + uint32_t(3 * op_bytes + ew * 2 * ku::OUT_BYTES);
+    const uint32_t stg = sbase + uint32_t(3 * op_bytes + ew * ku::OUT_BYTES);
     const float s2 = float(hyp[2 * d]);
     const float l2s2 = __log2f(s2);
     const float kLog2e = 1.4426950408889634f;
     const double cmean = hyp[2 * d + 1];
-    const uint32_t tlane = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(half * 64);
-    const float* abase = alpha32 + half * 64;
+    const uint32_t tlane = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(colq * 32);
+    const float* abase = alpha32 + colq * 32;
     float m = 0.f;
-    // alpha of this warp's 64 columns, one block ahead (cp.async, per-warp double buffer): the values are used
-    // once per tile, so they always come from L2 and a register prefetch of one slab does not cover the latency
+    // alpha of this warp's 32 columns, one block ahead (cp.async, per-warp double buffer): the values are used
+    // once per tile, so they always come from L2
     float* alw = &al_sh[ew][0][0];
     auto alpha_fetch = [&](int nb_, int buf_) {
-      if (lane < 16) {
-        const unsigned sa = smem_u32(alw + buf_ * 64 + lane * 4);
+      if (lane < 8) {
+        const unsigned sa = smem_u32(alw + buf_ * 32 + lane * 4);
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(abase + nb_ * ku::BN + lane * 4)
                      : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    // one 32 x 32 slab: values -> K*, mu partial, TF32 bits into the swizzled staging tile, TMA store
-    auto emit = [&](const uint32_t (&r)[32], const float* al, int sbuf, int col, int crow) {
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    const int my_tiles = (tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+    const int nblocks = my_tiles * nblk;     // 128 x 128 blocks this CTA produces, accumulators in ring order
+    uint32_t acc_phase = 0;
+    int acc = 0;
+    if (nblocks > 0) alpha_fetch(0, 0);
+    int tile = blockIdx.x, nb = 0, tcount = 0;
+    for (int blk = 0; blk < nblocks; ++blk) {
+      const int nb_next = (nb + 1 == nblk) ? 0 : nb + 1;
+      const float* al = alw + (blk & 1) * 32;
+      alpha_fetch(nb_next, (blk + 1) & 1);                       // next block's alpha (harmless after the last)
+      uint32_t r[32];
+      mbar_wait(&t_full[acc], acc_phase);
+      tc_fence_after();
+      tmem_ld32_issue(tlane + uint32_t(acc * ku::BN), r);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");      // this block's alpha has landed
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile is free again
       __syncwarp();
-      const uint32_t sdst = stg + uint32_t(sbuf * ku::OUT_BYTES + lane * 128);
+      tmem_ld_wait(r);
+      tc_fence_before();
+      mbar_arrive(&t_empty[acc]);
+      if (++acc == ku::ACCS) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+      // values -> K*, mu partial, TF32 bits into the swizzled staging tile, TMA store
+      const uint32_t sdst = stg + uint32_t(lane * 128);
 #pragma unroll
       for (int c4 = 0; c4 < 8; ++c4) {
         uint32_t u[4];
@@ -1878,56 +1905,18 @@ k_kstar_umma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                      : "memory");
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
+      __syncwarp();                          // staging tile complete; all lanes are done with al
       if (lane == 0) {
-        ku::tma_store_2d(&mapO, stg + uint32_t(sbuf * ku::OUT_BYTES), col, crow);
+        ku::tma_store_2d(&mapO, stg, nb * ku::BN + colq * 32, tile * ku::BM + quarter * 32);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
-    };
-    // Software pipeline: while slab g is processed, the TMEM load and the alpha loads of slab g+1 are in flight.
-    // Slabs alternate between the register sets (r0, al0) = columns [0,32) and (r1, al1) = columns [32,64) of
-    // this warp's half of the 128-column accumulator.
-    uint32_t r0[32], r1[32];
-    const int my_tiles = (tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
-    const int nblocks = my_tiles * nblk;     // 128 x 128 blocks this CTA produces, accumulators in ring order
-    uint32_t acc_phase = 0;
-    int acc = 0;
-    if (nblocks > 0) {
-      alpha_fetch(0, 0);
-      mbar_wait(&t_full[0], 0);
-      tc_fence_after();
-      tmem_ld32_issue(tlane, r0);
-    }
-    int tile = blockIdx.x, nb = 0, tcount = 0;
-    for (int blk = 0; blk < nblocks; ++blk) {
-      const int crow = tile * ku::BM + quarter * 32, col = nb * ku::BN + half * 64;
-      const int nb_next = (nb + 1 == nblk) ? 0 : nb + 1;
-      const float* al = alw + (blk & 1) * 64;
-      alpha_fetch(nb_next, (blk + 1) & 1);                       // next block's alpha (harmless after the last)
-      asm volatile("cp.async.wait_group 1;" ::: "memory");      // this block's alpha has landed
-      __syncwarp();
-      tmem_ld_wait(r0);
-      tmem_ld32_issue(tlane + uint32_t(acc * ku::BN + 32), r1);
-      emit(r0, al, 0, col, crow);
-      tmem_ld_wait(r1);
-      tc_fence_before();
-      mbar_arrive(&t_empty[acc]);            // both slabs of this accumulator are in registers
-      if (++acc == ku::ACCS) {
-        acc = 0;
-        acc_phase ^= 1;
-      }
-      if (blk + 1 < nblocks) {
-        mbar_wait(&t_full[acc], acc_phase);
-        tc_fence_after();
-        tmem_ld32_issue(tlane + uint32_t(acc * ku::BN), r0);
-      }
-      emit(r1, al + 32, 1, col + 32, crow);
-      __syncwarp();                          // all lanes are done with al before the buffer is refilled
       if (nb_next == 0) {
-        // mu = c + (columns of half 0) + (columns of half 1), fixed order
-        if (half == 1) mu_sh[tcount & 1][row] = m;
+        // mu = c + the four column slabs in a fixed order
+        if (colq > 0) mu_sh[tcount & 1][colq - 1][row] = m;
         asm volatile("bar.sync 1, %0;" ::"n"(ku::EPI_WARPS * 32) : "memory");
-        if (half == 0) mu[int64_t(tile) * ku::BM + row] = cmean + double(m + mu_sh[tcount & 1][row]);
+        if (colq == 0)
+          mu[int64_t(tile) * ku::BM + row] =
+              cmean + double(((m + mu_sh[tcount & 1][0][row]) + mu_sh[tcount & 1][1][row]) + mu_sh[tcount & 1][2][row]);
         m = 0.f;
         tile += gridDim.x;
         ++tcount;
