@@ -298,10 +298,14 @@ int bbo_gp_score_pool_host(const bbo_gp_state* st, const bbo_acq* acq, int32_t p
                        false, cs);
     if (rc != BBO_OK) { cleanup(); return rc; }
   }
+  // the first transfer is a single chunk, so that the kernels start after 1/BBO_HOST_STAGE_CHUNKS of a staging
+  // buffer has crossed PCIe; every later transfer is hidden behind the previous buffer's kernels
+  const int64_t q_first = qp / BBO_HOST_STAGE_CHUNKS;
   int64_t ci = 0;
-  for (int64_t c0 = 0; c0 < q; c0 += qp, ++ci) {
+  for (int64_t c0 = 0; c0 < q; ++ci) {
     const int buf = int(ci & 1);
-    const int64_t qc = (q - c0 < qp) ? q - c0 : qp;
+    const int64_t want = ci == 0 ? q_first : qp;
+    const int64_t qc = (q - c0 < want) ? q - c0 : want;
     char* dst = static_cast<char*>(staging_dev) + size_t(buf) * size_t(qp) * row;
     if (ci >= 2) BBO_HOST_CHECK(cudaStreamWaitEvent(copy, freed[buf], 0));
     BBO_HOST_CHECK(cudaMemcpyAsync(dst, static_cast<const char*>(Xq_host) + size_t(c0) * row, size_t(qc) * row,
@@ -313,6 +317,7 @@ int bbo_gp_score_pool_host(const bbo_gp_state* st, const bbo_acq* acq, int32_t p
                        ci > 0, cs);
     if (rc != BBO_OK) { cudaStreamSynchronize(copy); cleanup(); return rc; }
     BBO_HOST_CHECK(cudaEventRecord(freed[buf], cs));
+    c0 += qc;
   }
   BBO_HOST_CHECK(cudaMemcpyAsync(topk_score_host, topk_score_dev, size_t(k) * sizeof(double),
                                  cudaMemcpyDeviceToHost, cs));
