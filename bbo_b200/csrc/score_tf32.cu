@@ -579,7 +579,7 @@ __device__ __forceinline__ void commit_2sm(uint64_t* bar) {
 
 __global__ void __launch_bounds__(tf::THREADS, 1)
 k_vnorm_tf32_2sm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int np,
-                 int64_t qc_pad, double* __restrict__ vpart) {
+                 int64_t qc_pad, double* __restrict__ vpart, int shrink) {
   using namespace tf;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[tf2::STAGES], empty_bar[tf2::STAGES], tfull_bar[2], tempty_bar[2];
@@ -635,11 +635,17 @@ k_vnorm_tf32_2sm(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           tf2::mbar_expect_tx_cluster(
               lbar, tf2::A_BYTES + (act0 ? tf2::BH_BYTES : 0) + (has1 ? tf2::BH_BYTES : 0));
           tf2::tma_load_2d_2sm(sa, &mapA, lbar, k, c0);
+          // diagonal block, kk columns in: the MMA takes N = 256 - kk, i.e. the first 128 - kk/2 rows of either
+          // CTA's tile, and accumulator column c must stay physical row c: the second CTA's box starts kk/2 rows
+          // earlier (its first rows are then physical rows 128 - kk/2 ..)
+          const int sh0 = (shrink && k > b0 * tf2::BN) ? int(cta_rank) * ((k - b0 * tf2::BN) >> 1) : 0;
+          const int sh1 = (shrink && k > b1 * tf2::BN) ? int(cta_rank) * ((k - b1 * tf2::BN) >> 1) : 0;
           if (act0)
-            tf2::tma_load_2d_2sm(sa + tf2::A_BYTES, &mapB, lbar, k, b0 * tf2::BN + int(cta_rank) * (tf2::BN / 2));
+            tf2::tma_load_2d_2sm(sa + tf2::A_BYTES, &mapB, lbar, k,
+                                 b0 * tf2::BN + int(cta_rank) * (tf2::BN / 2) - sh0);
           if (has1)
             tf2::tma_load_2d_2sm(sa + tf2::A_BYTES + tf2::BH_BYTES, &mapB, lbar, k,
-                                 b1 * tf2::BN + int(cta_rank) * (tf2::BN / 2));
+                                 b1 * tf2::BN + int(cta_rank) * (tf2::BN / 2) - sh1);
           if (++stage == tf2::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -649,8 +655,16 @@ k_vnorm_tf32_2sm(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
   } else if (warp == 1) {
     if (lane == 0 && leader) {   // ===== MMA issuer (leader CTA only) =====
-      // D=f32, A=B=tf32, K-major, N=256, M=256 (two SMs)
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(tf2::BN >> 3) << 17) | (uint32_t(256 >> 4) << 24);
+      // D=f32, A=B=tf32, K-major, N=256, M=256 (two SMs).  In the diagonal 256 x 256 block of a row block the rows
+      // above the stage's first column are zero and sit at the end of the block (k_make_tf32): N shrinks by 16
+      // per stage there, so the diagonal blocks cost 17/32 of a full block instead of 1 (BBO_TF32_FULL_DIAG=1: off)
+      const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(256 >> 4) << 24);
+      const uint32_t idesc = idesc_base | (uint32_t(tf2::BN >> 3) << 17);
+      auto idesc_for = [&](int k, int b) -> uint32_t {
+        const int kk = k - b * tf2::BN;              // columns into the diagonal block (multiple of 16), < 0 above it
+        if (!shrink || kk <= 0) return idesc;
+        return idesc_base | (uint32_t((tf2::BN - kk) >> 3) << 17);
+      };
       int stage = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int b0 = blockIdx.y; b0 < nblk; b0 += 2 * S) {
@@ -669,17 +683,19 @@ k_vnorm_tf32_2sm(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           const uint64_t adesc = tfp::make_desc64(sa);
           if (act0) {
             const uint64_t bdesc = tfp::make_desc64(sa + tf2::A_BYTES);
+            const uint32_t id0 = idesc_for(k, b0);
 #pragma unroll
             for (int kk = 0; kk < tf2::BK / tf2::UK; ++kk)
-              tf2::mma_tf32_2sm(tmem_base, adesc + uint64_t(kk * 2), bdesc + uint64_t(kk * 2), idesc,
+              tf2::mma_tf32_2sm(tmem_base, adesc + uint64_t(kk * 2), bdesc + uint64_t(kk * 2), id0,
                                 (k | kk) != 0 ? 1u : 0u);
           }
           if (has1) {
             const uint64_t bdesc = tfp::make_desc64(sa + tf2::A_BYTES + tf2::BH_BYTES);
+            const uint32_t id1 = idesc_for(k, b1);
 #pragma unroll
             for (int kk = 0; kk < tf2::BK / tf2::UK; ++kk)
               tf2::mma_tf32_2sm(tmem_base + uint32_t(tf2::BN), adesc + uint64_t(kk * 2), bdesc + uint64_t(kk * 2),
-                                idesc, (k | kk) != 0 ? 1u : 0u);
+                                id1, (k | kk) != 0 ? 1u : 0u);
           }
           tf2::commit_2sm(&empty_bar[stage]);                        // frees the stage in both CTAs
           if (k + tf2::BK == kend0) tf2::commit_2sm(&tfull_bar[0]);   // block b0 complete in both halves
@@ -1953,12 +1969,19 @@ static size_t kstar_fast_smem(int d) {
   return sizeof(float) * (size_t(128) * LS + 2 * 64 * LS + 128 + 128 + 128);
 }
 
-// out (rows256, np): TF32-rounded copy of linv (np, np); rows >= np are zero so that every
-// 256-row TMA box of the B operand is fully in bounds.
-__global__ void k_make_tf32(int64_t valid, int64_t total, const double* __restrict__ in, float* __restrict__ out) {
+// out (rows256, np): TF32-rounded copy of linv (np, np); rows >= np are zero so that every 256-row TMA box of the
+// B operand is fully in bounds.  Inside each 256-row block the rows are stored in REVERSE order (physical row c holds
+// logical row 255 - c).  The panel only sums squares over the rows of a block, so their order is free, and this order
+// puts the rows that are structurally zero in the diagonal block (logical row < column) at the END: for the
+// 16-column stage starting kk columns into the diagonal block only the first 256 - kk physical rows are non-zero and
+// the tensor core is given N = 256 - kk instead of 256 (k_vnorm_tf32_2sm: accumulator column c = physical row c in
+// every stage).
+__global__ void k_make_tf32(int64_t np, int64_t total, const double* __restrict__ in, float* __restrict__ out) {
   int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < total) {
-    float f = i < valid ? static_cast<float>(in[i]) : 0.f;
+    const int64_t prow = i / np, col = i - prow * np;
+    const int64_t lrow = (prow >> 8) * 256 + 255 - (prow & 255);
+    float f = lrow < np ? static_cast<float>(in[lrow * np + col]) : 0.f;
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(f));
     out[i] = __uint_as_float(u);
@@ -1968,8 +1991,8 @@ __global__ void k_make_tf32(int64_t valid, int64_t total, const double* __restri
 int64_t tf32_rows(int64_t n) { return ceil_div(padded(n), tf::BN) * tf::BN; }
 
 int make_tf32(int64_t n, const double* linv, float* out, cudaStream_t st) {
-  const int64_t np = padded(n), valid = np * np, total = tf32_rows(n) * np;
-  k_make_tf32<<<unsigned(ceil_div(total, 256)), 256, 0, st>>>(valid, total, linv, out);
+  const int64_t np = padded(n), total = tf32_rows(n) * np;
+  k_make_tf32<<<unsigned(ceil_div(total, 256)), 256, 0, st>>>(np, total, linv, out);
   BBO_LAUNCH_CHECK();
   return BBO_OK;
 }
@@ -2356,8 +2379,9 @@ static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
     const int np_i = int(np);
     const int64_t qp_i = w.qp;
     double* vp = w.vpart;
+    static const int shrink = getenv("BBO_TF32_FULL_DIAG") == nullptr ? 1 : 0;
     if (two_sm)
-      BBO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_vnorm_tf32_2sm, mapA, mapB, np_i, qp_i, vp));
+      BBO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_vnorm_tf32_2sm, mapA, mapB, np_i, qp_i, vp, shrink));
     else
       BBO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_vnorm_tf32_pair<2>, mapA, mapB, np_i, qp_i, vp));
   } else if (pair)
