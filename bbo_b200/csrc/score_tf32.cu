@@ -2403,9 +2403,16 @@ int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const vo
   Tf32Aux* aux = nullptr;
   int rc = get_aux(&aux);
   if (rc != BBO_OK) return rc;
-  // K* (FP32 pipe) and the tcgen05 panel both saturate shared-memory bandwidth, so running them
-  // concurrently gains nothing on B200 (measured: 40.7 vs 40.6 ms/step); default is one stream.
-  static const bool no_overlap = getenv("BBO_TF32_OVERLAP") == nullptr;
+  // Two streams: K* of chunk i+1 is queued behind K* of chunk i on the auxiliary stream while the panel of chunk i
+  // runs on `st`.  Neither the tcgen05 K* producer (214 KB shared memory, 512 TMEM columns) nor the panel fits on an
+  // SM next to the other, so the K* CTAs only take the SMs the panel's last wave has left: they fill its tail
+  // (measured 35.4 -> 35.0 ms/step, twice, same box).  With the mma.sync producers, which do share SMs with the
+  // panel, the overlap gained nothing (40.7 vs 40.6 ms/step: both saturate shared-memory bandwidth), so they stay
+  // on one stream.  BBO_TF32_OVERLAP=1 / BBO_TF32_NO_OVERLAP=1 force either schedule.
+  static const bool force_on = getenv("BBO_TF32_OVERLAP") != nullptr;
+  static const bool force_off = getenv("BBO_TF32_NO_OVERLAP") != nullptr;
+  // (the per-kernel CUDA-event regions of bbo_profile_* are only meaningful on one stream: profiling forces it)
+  const bool no_overlap = force_off || prof_enabled() || (!force_on && !use_kstar_umma(s.h.d));
   Tf32Aux serial;
   if (no_overlap) {
     serial = *aux;
