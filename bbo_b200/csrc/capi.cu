@@ -263,40 +263,48 @@ int bbo_gp_score_pool_host(const bbo_gp_state* st, const bbo_acq* acq, int32_t p
   if ((q > 0 && !Xq_host) || !topk_score_host || !topk_index_host || !staging_dev || !topk_score_dev ||
       !topk_index_dev || q_chunk < 1 || q < 0)
     return BBO_ERR_BAD_ARG;
-  cudaStream_t cs = S(stream), copy = nullptr;
-  cudaEvent_t ready[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
+  cudaStream_t cs = S(stream);
+  // copy stream and hand-over events: created once per device (creating and destroying them per call costs a few
+  // tens of microseconds and a driver lock per suggestion)
+  struct HostAux {
+    cudaStream_t copy = nullptr;
+    cudaEvent_t ready[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
+  };
+  static HostAux g_host_aux[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return BBO_ERR_BAD_ARG;
+  HostAux& ha = g_host_aux[dev];
   // one staging buffer = BBO_HOST_STAGE_CHUNKS scoring chunks, so that the K*/panel pipeline inside
   // gp_score_pool has several chunks to overlap
   const int64_t qp = BBO_HOST_STAGE_CHUNKS * (q_chunk < 128 ? 128 : (q_chunk + 127) / 128 * 128);
   const size_t esz = xq_is_f32 ? sizeof(float) : sizeof(double);
   const size_t row = size_t(st->h.d) * esz;
   int rc = BBO_OK;
-  auto cleanup = [&]() {
-    for (int i = 0; i < 2; ++i) {
-      if (ready[i]) cudaEventDestroy(ready[i]);
-      if (freed[i]) cudaEventDestroy(freed[i]);
-    }
-    if (copy) cudaStreamDestroy(copy);
-  };
 #define BBO_HOST_CHECK(expr)                          \
   do {                                                \
     cudaError_t _e = (expr);                          \
     if (_e != cudaSuccess) {                          \
       rc = cuda_fail(_e, #expr);                      \
-      cleanup();                                      \
       return rc;                                      \
     }                                                 \
   } while (0)
-  BBO_HOST_CHECK(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; ++i) {
-    BBO_HOST_CHECK(cudaEventCreateWithFlags(&ready[i], cudaEventDisableTiming));
-    BBO_HOST_CHECK(cudaEventCreateWithFlags(&freed[i], cudaEventDisableTiming));
+  if (!ha.copy) {
+    BBO_HOST_CHECK(cudaStreamCreateWithFlags(&ha.copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      BBO_HOST_CHECK(cudaEventCreateWithFlags(&ha.ready[i], cudaEventDisableTiming));
+      BBO_HOST_CHECK(cudaEventCreateWithFlags(&ha.freed[i], cudaEventDisableTiming));
+    }
   }
+  cudaStream_t copy = ha.copy;
+  cudaEvent_t* ready = ha.ready;
+  cudaEvent_t* freed = ha.freed;
+  // the staging buffers of an earlier call on another stream may still be in use
+  BBO_HOST_CHECK(cudaStreamSynchronize(copy));
   if (q == 0) {
     rc = gp_score_pool(*st, *acq, precision, staging_dev, xq_is_f32, 0, index_offset, k, topk_score_dev,
                        topk_index_dev, nullptr, nullptr, nullptr, nullptr, workspace_dev, workspace_bytes, q_chunk,
                        false, cs);
-    if (rc != BBO_OK) { cleanup(); return rc; }
+    if (rc != BBO_OK) return rc;
   }
   // the first transfer is a single chunk, so that the kernels start after 1/BBO_HOST_STAGE_CHUNKS of a staging
   // buffer has crossed PCIe; every later transfer is hidden behind the previous buffer's kernels
@@ -315,7 +323,7 @@ int bbo_gp_score_pool_host(const bbo_gp_state* st, const bbo_acq* acq, int32_t p
     rc = gp_score_pool(*st, *acq, precision, dst, xq_is_f32, qc, index_offset + c0, k, topk_score_dev,
                        topk_index_dev, nullptr, nullptr, nullptr, nullptr, workspace_dev, workspace_bytes, q_chunk,
                        ci > 0, cs);
-    if (rc != BBO_OK) { cudaStreamSynchronize(copy); cleanup(); return rc; }
+    if (rc != BBO_OK) { cudaStreamSynchronize(copy); return rc; }
     BBO_HOST_CHECK(cudaEventRecord(freed[buf], cs));
     c0 += qc;
   }
@@ -326,7 +334,6 @@ int bbo_gp_score_pool_host(const bbo_gp_state* st, const bbo_acq* acq, int32_t p
   BBO_HOST_CHECK(cudaStreamSynchronize(cs));
   BBO_HOST_CHECK(cudaStreamSynchronize(copy));
 #undef BBO_HOST_CHECK
-  cleanup();
   return BBO_OK;
 }
 
