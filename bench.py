@@ -397,6 +397,22 @@ def run_b200(a):
                 peak64 = peak
             fit["peak_tflops"] = peak64
             fit["frac"] = fit["achieved_tflops"] / peak64
+            # the same iteration inside GP.train (gp.py:54-63): value + gradient + Adam update per epoch, the epoch
+            # replayed as a CUDA graph (what a suggest() pays 100 times); second train() call timed, 20 epochs
+            cov_t = B.ScaleKernel(B.RBFKernel(ard_dim=a.d)).double()
+            with torch.no_grad():
+                cov_t.base_kernel.lengthscale.fill_(raw_ls)
+                cov_t.variance.fill_(raw_var)
+            gpt = B.CudaGP(torch.as_tensor(X), torch.as_tensor(y).reshape(-1, 1), B.ConstantMean().double(), cov_t,
+                           device=dev, noise_variance=NOISE, epochs=20)
+            gpt.train()
+            torch.cuda.synchronize()
+            f0.record()
+            gpt.train()
+            f1.record()
+            torch.cuda.synchronize()
+            fit["train_ms_per_epoch"] = f0.elapsed_time(f1) / 20
+            del gpt
 
         # ---- CPU baseline on this host's cores (bounded sample; N=1 only)
         if world == 1 and not a.no_cpu:
