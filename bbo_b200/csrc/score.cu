@@ -603,34 +603,35 @@ int gp_score_pool(const bbo_gp_state& s, const bbo_acq& acq, int precision, cons
     BBO_LAUNCH_CHECK();
   }
   // acquisition + running top-k of one finished chunk (mu and |v|^2 partials are ready on st)
-  auto consume = [&](int64_t c0, int64_t qc, const double* mu_chunk, int nsplit) -> int {
-    prof_begin(kProfSelect, st);
+  auto consume = [&](int64_t c0, int64_t qc, const double* mu_chunk, int nsplit, const double* vpart,
+                     cudaStream_t sc) -> int {
+    prof_begin(kProfSelect, sc);
     const int64_t nb = ceil_div(qc, kSeg);
     static const bool unfused = getenv("BBO_SELECT_UNFUSED") != nullptr;
     if (!unfused && (nb + 1) * k <= kSeg) {
       // fused acquisition + per-segment top-k, then one merge with the running list (2 launches per chunk)
-      k_acq_topk<<<unsigned(nb), 256, 0, st>>>(
-          s.h, acq, precision == BBO_PREC_TF32, s.hyp, mu_chunk, w.vpart, nsplit, w.qp, qc, index_offset + c0, k,
+      k_acq_topk<<<unsigned(nb), 256, 0, sc>>>(
+          s.h, acq, precision == BBO_PREC_TF32, s.hyp, mu_chunk, vpart, nsplit, w.qp, qc, index_offset + c0, k,
           mu_out ? mu_out + c0 : nullptr, var_out ? var_out + c0 : nullptr, score_out ? score_out + c0 : nullptr,
           nan_count, w.la_s, w.la_i, nullptr);
       BBO_LAUNCH_CHECK();
-      k_topk_merge_running<<<1, 256, 0, st>>>(w.la_s, w.la_i, int(nb * k), k, topk_s, topk_i);
+      k_topk_merge_running<<<1, 256, 0, sc>>>(w.la_s, w.la_i, int(nb * k), k, topk_s, topk_i);
       BBO_LAUNCH_CHECK();
     } else {
-      k_acq<<<unsigned(ceil_div(qc, 256)), 256, 0, st>>>(
-          s.h, acq, 1, precision == BBO_PREC_TF32, s.hyp, mu_chunk, w.vpart, nsplit, w.qp, qc, w.score,
+      k_acq<<<unsigned(ceil_div(qc, 256)), 256, 0, sc>>>(
+          s.h, acq, 1, precision == BBO_PREC_TF32, s.hyp, mu_chunk, vpart, nsplit, w.qp, qc, w.score,
           mu_out ? mu_out + c0 : nullptr, var_out ? var_out + c0 : nullptr, score_out ? score_out + c0 : nullptr,
           nan_count);
       BBO_LAUNCH_CHECK();
       // level 1: segments of this chunk -> list A (after the k running entries)
-      BBO_CUDA_CHECK(cudaMemcpyAsync(w.la_s, topk_s, size_t(k) * sizeof(double), cudaMemcpyDeviceToDevice, st));
-      BBO_CUDA_CHECK(cudaMemcpyAsync(w.la_i, topk_i, size_t(k) * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
-      k_topk_seg<<<unsigned(nb), 256, 0, st>>>(w.score, nullptr, index_offset + c0, qc, k, w.la_s + k, w.la_i + k);
+      BBO_CUDA_CHECK(cudaMemcpyAsync(w.la_s, topk_s, size_t(k) * sizeof(double), cudaMemcpyDeviceToDevice, sc));
+      BBO_CUDA_CHECK(cudaMemcpyAsync(w.la_i, topk_i, size_t(k) * sizeof(int64_t), cudaMemcpyDeviceToDevice, sc));
+      k_topk_seg<<<unsigned(nb), 256, 0, sc>>>(w.score, nullptr, index_offset + c0, qc, k, w.la_s + k, w.la_i + k);
       BBO_LAUNCH_CHECK();
-      int rc2 = topk_levels(w.la_s, w.la_i, (nb + 1) * k, w.lb_s, w.lb_i, k, topk_s, topk_i, st);
+      int rc2 = topk_levels(w.la_s, w.la_i, (nb + 1) * k, w.lb_s, w.lb_i, k, topk_s, topk_i, sc);
       if (rc2 != BBO_OK) return rc2;
     }
-    prof_end(kProfSelect, st);
+    prof_end(kProfSelect, sc);
     return BBO_OK;
   };
   if (precision == BBO_PREC_TF32) return q == 0 ? BBO_OK : score_tf32_pipeline(s, w, Xq, xq_is_f32, q, consume, st);
@@ -641,7 +642,7 @@ int gp_score_pool(const bbo_gp_state& s, const bbo_acq& acq, int precision, cons
     int nsplit = 1;
     rc = posterior_chunk(s, w, precision, xq, xq_is_f32, qc, &nsplit, st);
     if (rc != BBO_OK) return rc;
-    rc = consume(c0, qc, w.mu, nsplit);
+    rc = consume(c0, qc, w.mu, nsplit, w.vpart, st);
     if (rc != BBO_OK) return rc;
   }
   return BBO_OK;

@@ -40,10 +40,11 @@ int topk_merge(const double* score, const int64_t* index, int64_t m, int k, doub
                cudaStream_t st);
 
 // TF32 mode (score_tf32.cu): pipelined K* (aux stream) / tcgen05 panel (st) over all chunks of a pool;
-// consume(chunk_start, qc, mu, nsplit) enqueues the per-chunk acquisition / selection work on st.
+// consume(chunk_start, qc, mu, nsplit, vpart, stream) enqueues the per-chunk acquisition / selection work.
+using ConsumeFn = std::function<int(int64_t, int64_t, const double*, int, const double*, cudaStream_t)>;
 size_t score_tf32_extra_bytes(int64_t n, int64_t d, int64_t qp);
 int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const void* Xq, int xq_is_f32, int64_t q,
-                        const std::function<int(int64_t, int64_t, const double*, int)>& consume, cudaStream_t st);
+                        const ConsumeFn& consume, cudaStream_t st);
 int make_tf32(int64_t n, const double* linv, float* out, cudaStream_t st);
 int64_t tf32_rows(int64_t n);
 

@@ -2090,8 +2090,10 @@ static int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t col
 
 // auxiliary stream + events of the K* / panel software pipeline (created once per device)
 struct Tf32Aux {
-  cudaStream_t sk = nullptr;
-  cudaEvent_t entry = nullptr, kdone[2] = {nullptr, nullptr}, pdone[2] = {nullptr, nullptr};
+  cudaStream_t sk = nullptr;   // K* producer
+  cudaStream_t ss = nullptr;   // acquisition + selection
+  cudaEvent_t entry = nullptr, kdone[2] = {nullptr, nullptr}, pdone[2] = {nullptr, nullptr},
+              sdone[2] = {nullptr, nullptr};
 };
 static Tf32Aux g_aux[16];
 static int get_aux(Tf32Aux** out) {
@@ -2101,10 +2103,12 @@ static int get_aux(Tf32Aux** out) {
   Tf32Aux& a = g_aux[dev];
   if (!a.sk) {
     BBO_CUDA_CHECK(cudaStreamCreateWithFlags(&a.sk, cudaStreamNonBlocking));
+    BBO_CUDA_CHECK(cudaStreamCreateWithFlags(&a.ss, cudaStreamNonBlocking));
     BBO_CUDA_CHECK(cudaEventCreateWithFlags(&a.entry, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
       BBO_CUDA_CHECK(cudaEventCreateWithFlags(&a.kdone[i], cudaEventDisableTiming));
       BBO_CUDA_CHECK(cudaEventCreateWithFlags(&a.pdone[i], cudaEventDisableTiming));
+      BBO_CUDA_CHECK(cudaEventCreateWithFlags(&a.sdone[i], cudaEventDisableTiming));
     }
   }
   *out = &a;
@@ -2331,7 +2335,7 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
 }
 
 static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf32Scratch& t, int buf,
-                        int64_t qc_pad, int* nsplit_out, cudaStream_t st) {
+                        int64_t qc_pad, double* vpart, int* nsplit_out, cudaStream_t st) {
   static DeviceOnce attr_once;
   if (attr_once.first())
     BBO_CUDA_CHECK(cudaFuncSetAttribute(k_vnorm_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, tf::SMEM_BYTES));
@@ -2378,7 +2382,7 @@ static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
     cfg.numAttrs = 1;
     const int np_i = int(np);
     const int64_t qp_i = w.qp;
-    double* vp = w.vpart;
+    double* vp = vpart;
     static const int shrink = getenv("BBO_TF32_FULL_DIAG") == nullptr ? 1 : 0;
     if (two_sm)
       BBO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_vnorm_tf32_2sm, mapA, mapB, np_i, qp_i, vp, shrink));
@@ -2386,20 +2390,24 @@ static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
       BBO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_vnorm_tf32_pair<2>, mapA, mapB, np_i, qp_i, vp));
   } else if (pair)
     k_vnorm_tf32_pair<1><<<dim3(unsigned(tiles), unsigned(nsplit)), tf::THREADS, tfp::SMEM_BYTES, st>>>(
-        mapA, mapB, int(np), w.qp, w.vpart);
+        mapA, mapB, int(np), w.qp, vpart);
   else
     k_vnorm_tf32<<<dim3(unsigned(tiles), unsigned(nsplit)), tf::THREADS, tf::SMEM_BYTES, st>>>(mapA, mapB, int(np),
-                                                                                              w.qp, w.vpart);
+                                                                                              w.qp, vpart);
   BBO_LAUNCH_CHECK();
   prof_end(kProfTf32, st);
   return BBO_OK;
 }
 
-// Software pipeline over the chunks of one pool: K* of chunk i+1 runs on the auxiliary stream
-// (FP32 pipe) while the tcgen05 panel of chunk i runs on `st` (tensor pipe).  `consume(c0, qc, mu,
-// nsplit)` enqueues the acquisition / top-k work of a finished chunk on `st`.
+// Software pipeline over the chunks of one pool.  Three streams when the tcgen05 K* producer is in use:
+//   sk   K*(i+1)                      queued behind K*(i); its CTAs fill the tail of panel(i)
+//   st   panel(i)                     back to back: nothing else sits between two panels
+//   ss   acquisition + top-k of (i)   small kernels that share the SMs with panel(i+1)
+// Buffers are double: Ks / mu (written by K*), the |v|^2 partial sums (written by the panel; slots 0-3 and 4-7 of
+// w.vpart).  K*(i+2) waits for panel(i) (Ks) and selection(i) (mu); panel(i+2) follows K*(i+2), hence also
+// selection(i) (partial sums).  `consume(c0, qc, mu, nsplit, vpart, stream)` enqueues the acquisition / top-k work.
 int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const void* Xq, int xq_is_f32, int64_t q,
-                        const std::function<int(int64_t, int64_t, const double*, int)>& consume, cudaStream_t st) {
+                        const ConsumeFn& consume, cudaStream_t st) {
   Tf32Aux* aux = nullptr;
   int rc = get_aux(&aux);
   if (rc != BBO_OK) return rc;
@@ -2455,9 +2463,11 @@ int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const vo
   }
   // one stream (default): stream order already is the dependency chain, no events needed
   const bool two_streams = aux->sk != st;
+  cudaStream_t ssel = two_streams ? aux->ss : st;
   if (two_streams) {
     BBO_CUDA_CHECK(cudaEventRecord(aux->entry, st));
     BBO_CUDA_CHECK(cudaStreamWaitEvent(aux->sk, aux->entry, 0));
+    BBO_CUDA_CHECK(cudaStreamWaitEvent(aux->ss, aux->entry, 0));
   }
   const int64_t nchunk = ceil_div(q, w.qp);
   auto chunk_len = [&](int64_t i) { return (q - i * w.qp < w.qp) ? q - i * w.qp : w.qp; };
@@ -2472,8 +2482,10 @@ int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const vo
     const int buf = int(i & 1);
     if (i + 1 < nchunk) {
       const int nb = buf ^ 1;
-      if (two_streams && i >= 1)
-        BBO_CUDA_CHECK(cudaStreamWaitEvent(aux->sk, aux->pdone[nb], 0));   // chunk i-1 released buffer nb
+      if (two_streams && i >= 1) {   // chunk i-1 released buffer nb: panel (Ks) and selection (mu, partial sums)
+        BBO_CUDA_CHECK(cudaStreamWaitEvent(aux->sk, aux->pdone[nb], 0));
+        BBO_CUDA_CHECK(cudaStreamWaitEvent(aux->sk, aux->sdone[nb], 0));
+      }
       const int64_t qn = chunk_len(i + 1);
       rc = launch_kstar(s, w, t, nb, chunk_ptr(i + 1), xq_is_f32, qn, ceil_div(qn, 128) * 128, aux->sk);
       if (rc != BBO_OK) return rc;
@@ -2482,11 +2494,19 @@ int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const vo
     const int64_t qc = chunk_len(i);
     if (two_streams) BBO_CUDA_CHECK(cudaStreamWaitEvent(st, aux->kdone[buf], 0));
     int nsplit = 1;
-    rc = launch_panel(s, w, t, buf, ceil_div(qc, 128) * 128, &nsplit, st);
+    double* vpart = w.vpart + int64_t(buf) * 4 * w.qp;
+    rc = launch_panel(s, w, t, buf, ceil_div(qc, 128) * 128, vpart, &nsplit, st);
     if (rc != BBO_OK) return rc;
-    rc = consume(i * w.qp, qc, t.mu[buf], nsplit);
+    if (two_streams) {
+      BBO_CUDA_CHECK(cudaEventRecord(aux->pdone[buf], st));
+      BBO_CUDA_CHECK(cudaStreamWaitEvent(ssel, aux->pdone[buf], 0));
+    }
+    rc = consume(i * w.qp, qc, t.mu[buf], nsplit, vpart, ssel);
     if (rc != BBO_OK) return rc;
-    if (two_streams) BBO_CUDA_CHECK(cudaEventRecord(aux->pdone[buf], st));
+    if (two_streams) BBO_CUDA_CHECK(cudaEventRecord(aux->sdone[buf], ssel));
+  }
+  if (two_streams) {   // the caller's stream sees the finished selection
+    BBO_CUDA_CHECK(cudaStreamWaitEvent(st, aux->sdone[int((nchunk - 1) & 1)], 0));
   }
   return BBO_OK;
 }
