@@ -210,6 +210,24 @@ __device__ __forceinline__ T acq_value(const bbo_acq& a, T mu, T sd) {
   return imp * Phi + sd * phi;
 }
 
+// |v|^2 of candidate c from its partial sums.  nsplit >= 0: that many slots, added in order.  nsplit < 0: one slot per
+// 256-row block (-nsplit of them, persistent TF32 panel), added with the association of the four-slot form -- slot s
+// of that form is the in-order sum of the blocks b = s, s+4, ... -- so both forms give the same bits.
+__device__ __forceinline__ double sum_vpart(const double* __restrict__ vpart, int nsplit, int64_t qc_pad, int64_t c) {
+  double vn = 0.0;
+  if (nsplit >= 0) {
+    for (int s = 0; s < nsplit; ++s) vn += vpart[int64_t(s) * qc_pad + c];
+  } else {
+    const int nb = -nsplit;
+    for (int s = 0; s < 4; ++s) {
+      double t = 0.0;
+      for (int b = s; b < nb; b += 4) t += vpart[int64_t(b) * qc_pad + c];
+      vn += t;
+    }
+  }
+  return vn;
+}
+
 __global__ void __launch_bounds__(256)
 k_acq(bbo_gp_hyper h, bbo_acq a, int has_acq, int clamp_var, const double* __restrict__ hyp,
       const double* __restrict__ mu, const double* __restrict__ vpart, int nsplit, int64_t qc_pad, int64_t qc,
@@ -219,8 +237,7 @@ k_acq(bbo_gp_hyper h, bbo_acq a, int has_acq, int clamp_var, const double* __res
   if (c >= qc) return;
   const double eps = h.kind == BBO_KERNEL_MATERN52 ? h.pairwise_eps : 0.0;
   const double kxx = hyp[2 * h.d] * kernel_from_s(h.kind, double(h.d) * eps * eps);
-  double vn = 0.0;
-  for (int s = 0; s < nsplit; ++s) vn += vpart[int64_t(s) * qc_pad + c];
+  const double vn = sum_vpart(vpart, nsplit, qc_pad, c);
   double var = kxx - vn + h.noise;
   if (clamp_var) var = fmax(var, 0.0);
   const double m = mu[c];
@@ -362,8 +379,7 @@ k_acq_topk(bbo_gp_hyper h, bbo_acq a, int clamp_var, const double* __restrict__ 
     double sc = -INFINITY;
     int64_t ix = -1;
     if (c < qc) {
-      double vn = 0.0;
-      for (int s = 0; s < nsplit; ++s) vn += vpart[int64_t(s) * qc_pad + c];
+      const double vn = sum_vpart(vpart, nsplit, qc_pad, c);
       double var = kxx - vn + h.noise;
       if (clamp_var) var = fmax(var, 0.0);
       const double m = mu[c];

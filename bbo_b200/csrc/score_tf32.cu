@@ -577,9 +577,10 @@ __device__ __forceinline__ void commit_2sm(uint64_t* bar) {
 }
 }  // namespace tf2
 
+template <bool PERSIST>
 __global__ void __launch_bounds__(tf::THREADS, 1)
 k_vnorm_tf32_2sm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int np,
-                 int64_t qc_pad, double* __restrict__ vpart, int shrink) {
+                 int64_t qc_pad, double* __restrict__ vpart, int shrink, const int* __restrict__ sched, int maxj) {
   using namespace tf;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[tf2::STAGES], empty_bar[tf2::STAGES], tfull_bar[2], tempty_bar[2];
@@ -590,9 +591,25 @@ k_vnorm_tf32_2sm(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  const int c0 = blockIdx.x * tf2::BM;
   const int nblk = (np + tf2::BN - 1) / tf2::BN;
   const int S = gridDim.y;
+  // Work of this CTA pair.  Legacy form: the candidate tile blockIdx.x and the row-block pairs (b0, b0 + S),
+  // b0 = blockIdx.y, blockIdx.y + 2S, ...  Persistent form: item j of the pair's list in `sched`
+  // (k_panel_schedule): item = 64 * tile pair + row pair r, row blocks (2r, 2r + 1); -1 ends the list.
+  auto item_at = [&](int j, int& b0, int& b1, int& c0) -> bool {
+    if (PERSIST) {
+      const int it = __ldg(sched + int64_t(blockIdx.x >> 1) * maxj + j);
+      if (it < 0) return false;
+      c0 = ((it >> 6) * 2 + int(cta_rank)) * tf2::BM;
+      b0 = (it & 63) * 2;
+      b1 = b0 + 1;
+      return true;
+    }
+    b0 = int(blockIdx.y) + 2 * S * j;
+    b1 = b0 + S;
+    c0 = int(blockIdx.x) * tf2::BM;
+    return b0 < nblk;
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < tf2::STAGES; ++s) {
@@ -622,8 +639,9 @@ k_vnorm_tf32_2sm(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (lane == 0) {   // ===== TMA producer (both CTAs) =====
       int stage = 0;
       uint32_t phase = 0;
-      for (int b0 = blockIdx.y; b0 < nblk; b0 += 2 * S) {
-        const int b1 = b0 + S;
+      for (int j = 0;; ++j) {
+        int b0, b1, c0;
+        if (!item_at(j, b0, b1, c0)) break;
         const bool has1 = b1 < nblk;
         const int kend0 = min((b0 + 1) * tf2::BN, np);
         const int kend = has1 ? min((b1 + 1) * tf2::BN, np) : kend0;
@@ -666,14 +684,15 @@ k_vnorm_tf32_2sm(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         return idesc_base | (uint32_t((tf2::BN - kk) >> 3) << 17);
       };
       int stage = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      for (int b0 = blockIdx.y; b0 < nblk; b0 += 2 * S) {
-        const int b1 = b0 + S;
+      uint32_t phase = 0, acc_phase = 0, acc1_phase = 0;   // the second accumulator idles in an item without b1
+      for (int j = 0;; ++j) {
+        int b0, b1, c0;
+        if (!item_at(j, b0, b1, c0)) break;
         const bool has1 = b1 < nblk;
         const int kend0 = min((b0 + 1) * tf2::BN, np);
         const int kend = has1 ? min((b1 + 1) * tf2::BN, np) : kend0;
         mbar_wait(&tempty_bar[0], acc_phase ^ 1);
-        if (has1) mbar_wait(&tempty_bar[1], acc_phase ^ 1);
+        if (has1) mbar_wait(&tempty_bar[1], acc1_phase ^ 1);
         tc_fence_after();
         for (int k = 0; k < kend; k += tf2::BK) {
           const bool act0 = k < kend0;
@@ -704,7 +723,10 @@ k_vnorm_tf32_2sm(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             phase ^= 1;
           }
         }
-        if (has1) tf2::commit_2sm(&tfull_bar[1]);
+        if (has1) {
+          tf2::commit_2sm(&tfull_bar[1]);
+          acc1_phase ^= 1;
+        }
         acc_phase ^= 1;
       }
     }
@@ -712,13 +734,16 @@ k_vnorm_tf32_2sm(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     double tot0 = 0.0, tot1 = 0.0, tot2 = 0.0, tot3 = 0.0;
-    uint32_t acc_phase = 0;
-    for (int b0 = blockIdx.y; b0 < nblk; b0 += 2 * S) {
+    uint32_t acc_ph[2] = {0, 0};
+    for (int j = 0;; ++j) {
+      int b0, b1, c0;
+      if (!item_at(j, b0, b1, c0)) break;
 #pragma unroll
       for (int a = 0; a < 2; ++a) {
-        const int nb = b0 + a * S;
+        const int nb = a == 0 ? b0 : b1;
         if (nb >= nblk) break;
-        mbar_wait(&tfull_bar[a], acc_phase);
+        mbar_wait(&tfull_bar[a], acc_ph[a]);
+        acc_ph[a] ^= 1;
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(a * tf2::BN);
         float part = 0.f;
@@ -736,20 +761,26 @@ k_vnorm_tf32_2sm(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           }
           part += (s0 + s1) + (s2 + s3);
         }
-        const int slot = nb & 3;
-        if (slot == 0) tot0 += double(part);
-        else if (slot == 1) tot1 += double(part);
-        else if (slot == 2) tot2 += double(part);
-        else tot3 += double(part);
+        if (PERSIST) {   // one slot per row block; k_acq / k_acq_topk add them with the four-slot association
+          vpart[int64_t(nb) * qc_pad + c0 + row] = double(part);
+        } else {
+          const int slot = nb & 3;
+          if (slot == 0) tot0 += double(part);
+          else if (slot == 1) tot1 += double(part);
+          else if (slot == 2) tot2 += double(part);
+          else tot3 += double(part);
+        }
         tc_fence_before();
         tf2::mbar_arrive_cluster(tf2::map_to_cta(smem_u32(&tempty_bar[a]), 0));   // leader's barrier
       }
-      acc_phase ^= 1;
     }
-    const double tots[4] = {tot0, tot1, tot2, tot3};
+    if (!PERSIST) {
+      const int c0 = int(blockIdx.x) * tf2::BM;
+      const double tots[4] = {tot0, tot1, tot2, tot3};
 #pragma unroll
-    for (int g4 = 0; g4 < 4; ++g4)
-      if (g4 % S == int(blockIdx.y)) vpart[int64_t(g4) * qc_pad + c0 + row] = tots[g4];
+      for (int g4 = 0; g4 < 4; ++g4)
+        if (g4 % S == int(blockIdx.y)) vpart[int64_t(g4) * qc_pad + c0 + row] = tots[g4];
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -758,6 +789,60 @@ k_vnorm_tf32_2sm(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Work list of the persistent panel (one warp).  Items (tile pair tp, row pair r) cost ~(r + 1) units (row blocks
+// 2r and 2r + 1 contract 512 (r + 1) columns of K*).  They are taken in an order that keeps the pairs that are in
+// flight at any time on FEW K* strips -- groups of `gs` tile pairs, inside a group the long row pairs first -- and
+// dealt by list scheduling: every item goes to the CTA pair with the least work so far (lowest index on ties).
+// That is what a run-time work queue would do under this cost model, without any in-kernel hand-over.  The K*
+// strip of a tile pair (256 x np floats) is read by all of its row pairs while it is still in L2, instead of
+// 4.5 times from HBM.  sched[c * maxj + j] = 64 tp + r, -1 terminated.
+// ------------------------------------------------------------------------------------------
+__global__ void k_panel_schedule(int ntp, int nrp, int nc, int gs, int maxj, int* __restrict__ sched) {
+  const int lane = threadIdx.x;
+  int load[3] = {0, 0, 0}, cnt[3] = {0, 0, 0};   // clusters lane, lane + 32, lane + 64
+  for (int g0 = 0; g0 < ntp; g0 += gs) {
+    const int ge = min(g0 + gs, ntp);
+    for (int r = nrp - 1; r >= 0; --r) {
+      for (int tp = g0; tp < ge; ++tp) {
+        // arg-min of the loads (lowest cluster index on ties)
+        int best = 0x7fffffff, bc = 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int c = lane + 32 * i;
+          if (c < nc && load[i] < best) {
+            best = load[i];
+            bc = c;
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const int ob = __shfl_xor_sync(0xffffffffu, best, o), oc = __shfl_xor_sync(0xffffffffu, bc, o);
+          if (ob < best || (ob == best && oc < bc)) {
+            best = ob;
+            bc = oc;
+          }
+        }
+        if ((bc & 31) == lane) {
+          const int i = bc >> 5;
+#pragma unroll
+          for (int ii = 0; ii < 3; ++ii)
+            if (ii == i) {
+              if (cnt[ii] < maxj - 1) sched[int64_t(bc) * maxj + cnt[ii]] = tp * 64 + r;
+              cnt[ii] += 1;
+              load[ii] += 4 * (r + 1) + 1;
+            }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nc) sched[int64_t(c) * maxj + min(cnt[i], maxj - 1)] = -1;
   }
 }
 
@@ -2014,7 +2099,9 @@ struct Tf32Scratch {
   uint32_t* Bfrag;   // candidate vectors of the current chunk in B-fragment order (third K* form)
   uint32_t* Aop;     // (qp, 96) candidate operand rows of the current chunk (fourth K* form, tcgen05)
   uint32_t* Bop;     // (np, 96) observation operand rows
+  double* vp32[2];   // (32, qp) |v|^2 partial sums, one slot per 256-row block (persistent panel), double-buffered
 };
+constexpr int64_t kSchedInts = 16384;   // work lists of the persistent panel (library-owned, see Tf32Aux)
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 size_t score_tf32_extra_bytes(int64_t n, int64_t d, int64_t qp) {
@@ -2024,7 +2111,7 @@ size_t score_tf32_extra_bytes(int64_t n, int64_t d, int64_t qp) {
          2 * align256(size_t(np) * (d + 16) * sizeof(uint32_t)) +
          align256(size_t(qp) * 2 * (d + 16) * sizeof(uint32_t)) +
          align256(size_t(qp) * 32 * ku::MAXBOX * sizeof(uint32_t)) +
-         align256(size_t(np) * 32 * ku::MAXBOX * sizeof(uint32_t)) + 256;
+         align256(size_t(np) * 32 * ku::MAXBOX * sizeof(uint32_t)) + 2 * align256(size_t(32) * qp * sizeof(double)) + 256;
 }
 
 static Tf32Scratch carve(const ScoreWorkspace& w, int64_t d) {
@@ -2053,6 +2140,11 @@ static Tf32Scratch carve(const ScoreWorkspace& w, int64_t d) {
   t.Aop = reinterpret_cast<uint32_t*>(p);
   p += align256(size_t(w.qp) * 32 * ku::MAXBOX * sizeof(uint32_t));
   t.Bop = reinterpret_cast<uint32_t*>(p);
+  p += align256(size_t(w.np) * 32 * ku::MAXBOX * sizeof(uint32_t));
+  for (int i = 0; i < 2; ++i) {
+    t.vp32[i] = reinterpret_cast<double*>(p);
+    p += align256(size_t(32) * w.qp * sizeof(double));
+  }
   return t;
 }
 
@@ -2094,6 +2186,11 @@ struct Tf32Aux {
   cudaStream_t ss = nullptr;   // acquisition + selection
   cudaEvent_t entry = nullptr, kdone[2] = {nullptr, nullptr}, pdone[2] = {nullptr, nullptr},
               sdone[2] = {nullptr, nullptr};
+  // work lists of the persistent panel: two cached shapes (a pool has full chunks and one last chunk), 2 x 64 KB of
+  // library-owned device memory per device, rebuilt by k_panel_schedule only when the shape changes
+  int* sched[2] = {nullptr, nullptr};
+  int64_t sched_key[2] = {0, 0};
+  int sched_next = 0;
 };
 static Tf32Aux g_aux[16];
 static int get_aux(Tf32Aux** out) {
@@ -2109,6 +2206,7 @@ static int get_aux(Tf32Aux** out) {
       BBO_CUDA_CHECK(cudaEventCreateWithFlags(&a.kdone[i], cudaEventDisableTiming));
       BBO_CUDA_CHECK(cudaEventCreateWithFlags(&a.pdone[i], cudaEventDisableTiming));
       BBO_CUDA_CHECK(cudaEventCreateWithFlags(&a.sdone[i], cudaEventDisableTiming));
+      BBO_CUDA_CHECK(cudaMalloc(&a.sched[i], size_t(kSchedInts) * sizeof(int)));
     }
   }
   *out = &a;
@@ -2334,8 +2432,10 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
   return BBO_OK;
 }
 
+// *vpart_out / *nsplit_out: where the partial sums of this chunk are and how k_acq / k_acq_topk add them (4 = the
+// four fixed slots of `vpart`; -nblk = one slot per row block in the persistent panel's own buffer).
 static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf32Scratch& t, int buf,
-                        int64_t qc_pad, double* vpart, int* nsplit_out, cudaStream_t st) {
+                        int64_t qc_pad, double* vpart, int* nsplit_out, double** vpart_out, cudaStream_t st) {
   static DeviceOnce attr_once;
   if (attr_once.first())
     BBO_CUDA_CHECK(cudaFuncSetAttribute(k_vnorm_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, tf::SMEM_BYTES));
@@ -2349,7 +2449,9 @@ static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
                                         tfp::SMEM_BYTES));
     BBO_CUDA_CHECK(cudaFuncSetAttribute(k_vnorm_tf32_pair<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         tfp::SMEM_BYTES));
-    BBO_CUDA_CHECK(cudaFuncSetAttribute(k_vnorm_tf32_2sm, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    BBO_CUDA_CHECK(cudaFuncSetAttribute(k_vnorm_tf32_2sm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        tf2::SMEM_BYTES));
+    BBO_CUDA_CHECK(cudaFuncSetAttribute(k_vnorm_tf32_2sm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         tf2::SMEM_BYTES));
   }
   const bool use_cluster = pair && clus && (qc_pad / tf::BM) % 2 == 0;
@@ -2366,6 +2468,7 @@ static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
   int64_t nsplit = tiles >= 148 ? 1 : (2 * tiles >= 148 ? 2 : 4);
   if (nblk < 2) nsplit = 1;
   *nsplit_out = 4;   // k_acq always sums the four slots
+  *vpart_out = vpart;
   prof_begin(kProfTf32, st);
   if (use_cluster) {
     cudaLaunchConfig_t cfg = {};
@@ -2384,8 +2487,36 @@ static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
     const int64_t qp_i = w.qp;
     double* vp = vpart;
     static const int shrink = getenv("BBO_TF32_FULL_DIAG") == nullptr ? 1 : 0;
-    if (two_sm)
-      BBO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_vnorm_tf32_2sm, mapA, mapB, np_i, qp_i, vp, shrink));
+    static const bool no_persist = getenv("BBO_TF32_NO_PERSIST") != nullptr;
+    const int ntp = int(tiles / 2), nrp = int((nblk + 1) / 2);
+    const int nc = ntp < sm_count() / 2 ? ntp : sm_count() / 2;
+    const int maxj = (ntp * nrp + nc - 1) / nc * 2 + 4;
+    if (two_sm && !no_persist && nblk >= 2 && nblk <= 32 && nc <= 96 && int64_t(nc) * maxj <= kSchedInts) {
+      // persistent form: one CTA pair per SM pair walks a work list (k_panel_schedule); one slot per row block
+      static const int64_t group_mb = getenv("BBO_TF32_PANEL_GROUP_MB") ? atoll(getenv("BBO_TF32_PANEL_GROUP_MB")) : 36;
+      const int gs_raw = int((group_mb << 20) / (int64_t(256) * np * 4));
+      const int gs = gs_raw < 1 ? 1 : gs_raw;
+      Tf32Aux* ax = nullptr;
+      rc = get_aux(&ax);
+      if (rc != BBO_OK) return rc;
+      const int64_t key = (int64_t(ntp) << 40) | (int64_t(nblk) << 24) | (int64_t(nc) << 12) | int64_t(gs);
+      int slot = ax->sched_key[0] == key ? 0 : (ax->sched_key[1] == key ? 1 : -1);
+      if (slot < 0) {   // (all users of a list are panels on `st`, stream-ordered behind this launch)
+        slot = ax->sched_next;
+        ax->sched_next ^= 1;
+        k_panel_schedule<<<1, 32, 0, st>>>(ntp, nrp, nc, gs, maxj, ax->sched[slot]);
+        BBO_LAUNCH_CHECK();
+        ax->sched_key[slot] = key;
+      }
+      cfg.gridDim = dim3(unsigned(2 * nc), 1);
+      const int* sc = ax->sched[slot];
+      double* vp32 = t.vp32[buf];
+      BBO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_vnorm_tf32_2sm<true>, mapA, mapB, np_i, qp_i, vp32, shrink, sc, maxj));
+      *nsplit_out = -int(nblk);
+      *vpart_out = vp32;
+    } else if (two_sm)
+      BBO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_vnorm_tf32_2sm<false>, mapA, mapB, np_i, qp_i, vp, shrink,
+                                        static_cast<const int*>(nullptr), 0));
     else
       BBO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_vnorm_tf32_pair<2>, mapA, mapB, np_i, qp_i, vp));
   } else if (pair)
@@ -2494,8 +2625,8 @@ int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const vo
     const int64_t qc = chunk_len(i);
     if (two_streams) BBO_CUDA_CHECK(cudaStreamWaitEvent(st, aux->kdone[buf], 0));
     int nsplit = 1;
-    double* vpart = w.vpart + int64_t(buf) * 4 * w.qp;
-    rc = launch_panel(s, w, t, buf, ceil_div(qc, 128) * 128, vpart, &nsplit, st);
+    double* vpart = nullptr;
+    rc = launch_panel(s, w, t, buf, ceil_div(qc, 128) * 128, w.vpart + int64_t(buf) * 4 * w.qp, &nsplit, &vpart, st);
     if (rc != BBO_OK) return rc;
     if (two_streams) {
       BBO_CUDA_CHECK(cudaEventRecord(aux->pdone[buf], st));
