@@ -795,7 +795,9 @@ k_vnorm_tf32_2sm(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 // ------------------------------------------------------------------------------------------
 // Work list of the persistent panel (one warp).  Items (tile pair tp, row pair r) cost ~(r + 1) units (row blocks
 // 2r and 2r + 1 contract 512 (r + 1) columns of K*).  They are taken in an order that keeps the pairs that are in
-// flight at any time on FEW K* strips -- groups of `gs` tile pairs, inside a group the long row pairs first -- and
+// flight at any time on FEW K* strips -- groups of `gs` tile pairs (default: strips of ~4 MB, i.e. one tile pair at
+// n = 4096; measured 32.65 / 32.83 / 32.86 / 34.4 ms per step for 4 / 9 / 13 / 36 MB), inside a group the long row
+// pairs first -- and
 // dealt by list scheduling: every item goes to the CTA pair with the least work so far (lowest index on ties).
 // That is what a run-time work queue would do under this cost model, without any in-kernel hand-over.  The K*
 // strip of a tile pair (256 x np floats) is read by all of its row pairs while it is still in L2, instead of
@@ -2493,7 +2495,7 @@ static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
     const int maxj = (ntp * nrp + nc - 1) / nc * 2 + 4;
     if (two_sm && !no_persist && nblk >= 2 && nblk <= 32 && nc <= 96 && int64_t(nc) * maxj <= kSchedInts) {
       // persistent form: one CTA pair per SM pair walks a work list (k_panel_schedule); one slot per row block
-      static const int64_t group_mb = getenv("BBO_TF32_PANEL_GROUP_MB") ? atoll(getenv("BBO_TF32_PANEL_GROUP_MB")) : 36;
+      static const int64_t group_mb = getenv("BBO_TF32_PANEL_GROUP_MB") ? atoll(getenv("BBO_TF32_PANEL_GROUP_MB")) : 4;
       const int gs_raw = int((group_mb << 20) / (int64_t(256) * np * 4));
       const int gs = gs_raw < 1 ? 1 : gs_raw;
       Tf32Aux* ax = nullptr;
