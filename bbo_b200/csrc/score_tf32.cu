@@ -2493,7 +2493,12 @@ static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
     const int ntp = int(tiles / 2), nrp = int((nblk + 1) / 2);
     const int nc = ntp < sm_count() / 2 ? ntp : sm_count() / 2;
     const int maxj = (ntp * nrp + nc - 1) / nc * 2 + 4;
-    if (two_sm && !no_persist && nblk >= 2 && nblk <= 32 && nc <= 96 && int64_t(nc) * maxj <= kSchedInts) {
+    // The persistent form trades the lock-step walk over the row pairs (which keeps the L^-1 blocks in flight few)
+    // for K* strip reuse: it needs the whole TF32 L^-1 resident in L2 next to the strips (n = 4096: 67 of 126 MB).
+    // At n = 8192 (268 MB) it was 9 % slower than the lock-step form, which therefore keeps the large problems.
+    const bool linv_fits_l2 = np * np * int64_t(sizeof(float)) <= (int64_t(80) << 20);
+    if (two_sm && !no_persist && linv_fits_l2 && nblk >= 2 && nblk <= 32 && nc <= 96 &&
+        int64_t(nc) * maxj <= kSchedInts) {
       // persistent form: one CTA pair per SM pair walks a work list (k_panel_schedule); one slot per row block
       static const int64_t group_mb = getenv("BBO_TF32_PANEL_GROUP_MB") ? atoll(getenv("BBO_TF32_PANEL_GROUP_MB")) : 4;
       const int gs_raw = int((group_mb << 20) / (int64_t(256) * np * 4));
