@@ -22,7 +22,7 @@ PREC_FP64, PREC_TF32 = 0, 1
 ROW_ALIGN = 128
 TOPK_MAX = 128
 APPEND_MAX = 32
-HOST_STAGE_CHUNKS = 4
+HOST_STAGE_CHUNKS = 8
 
 
 class GpHyper(C.Structure):

@@ -74,7 +74,7 @@ typedef enum bbo_precision { BBO_PREC_FP64 = 0, BBO_PREC_TF32 = 1 } bbo_precisio
 #define BBO_ROW_ALIGN 128   /* n is padded to a multiple of this in all n x n buffers */
 #define BBO_TOPK_MAX 128
 #define BBO_APPEND_MAX 32   /* observations appended per bbo_gp_append call */
-#define BBO_HOST_STAGE_CHUNKS 4   /* bbo_gp_score_pool_host copies this many chunks per H2D transfer */
+#define BBO_HOST_STAGE_CHUNKS 8   /* bbo_gp_score_pool_host copies this many chunks per H2D transfer */
 
 int bbo_version(void);
 /* text of the last CUDA error seen by this thread ("" if none) */
