@@ -29,8 +29,11 @@
  *
  * Conventions
  *   - plain pointers and sizes only; every pointer marked "dev" is CUDA device
- *     memory owned by the caller (the library never allocates device memory and
- *     keeps no global state); "host" pointers are host memory.
+ *     memory owned by the caller; "host" pointers are host memory.  All data buffers and
+ *     workspaces are the caller's.  The library itself keeps, per device and created on
+ *     first use, only scheduling aids: auxiliary streams and events (fit pipeline, TF32
+ *     scoring pipeline, host-pool copies) and 128 KB of device memory for the cached work
+ *     lists of the persistent TF32 panel.  One host thread per device.
  *   - all matrices row-major, contiguous; float64 unless stated.
  *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it
  *     unless the description says they synchronise.
