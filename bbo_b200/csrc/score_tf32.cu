@@ -17,7 +17,9 @@
 //                 Triangular: row block nb only contracts k < (nb+1)*256.
 // SASS evidence: UTCHMMA / UTMALDG / LDTM / SYNCS (see profiles/).
 #include <cuda.h>
+#include <vector>
 
+#include <cstdio>
 #include <cstdlib>
 #include <functional>
 
@@ -2092,7 +2094,7 @@ int make_tf32(int64_t n, const double* linv, float* out, cudaStream_t st) {
 //   Xs     (np, d)  float32  pre-scaled training inputs    alpha32 (np) float32
 struct Tf32Scratch {
   float* Ks[2];
-  double* mu[2];
+  double* mu[3];     // K* producers write mu of chunk i into mu[i % 3] (selection of chunk i runs up to two chunks later)
   float* Xs;
   float* bnorm;
   float* alpha32;
@@ -2108,7 +2110,7 @@ static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 size_t score_tf32_extra_bytes(int64_t n, int64_t d, int64_t qp) {
   const int64_t np = padded(n);
-  return 2 * align256(size_t(qp) * np * sizeof(float)) + align256(size_t(qp) * sizeof(double)) +
+  return 2 * align256(size_t(qp) * np * sizeof(float)) + 2 * align256(size_t(qp) * sizeof(double)) +
          align256(size_t(np) * d * sizeof(float)) + 2 * align256(size_t(np) * sizeof(float)) +
          2 * align256(size_t(np) * (d + 16) * sizeof(uint32_t)) +
          align256(size_t(qp) * 2 * (d + 16) * sizeof(uint32_t)) +
@@ -2126,6 +2128,8 @@ static Tf32Scratch carve(const ScoreWorkspace& w, int64_t d) {
   p += kb;
   t.mu[0] = w.mu;
   t.mu[1] = reinterpret_cast<double*>(p);
+  p += align256(size_t(w.qp) * sizeof(double));
+  t.mu[2] = reinterpret_cast<double*>(p);
   p += align256(size_t(w.qp) * sizeof(double));
   t.Xs = reinterpret_cast<float*>(p);
   p += align256(size_t(w.np) * d * sizeof(float));
@@ -2233,7 +2237,7 @@ static int sm_count() {
 }
 
 static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf32Scratch& t, int buf,
-                        const void* Xq, int xq_is_f32, int64_t qc, int64_t qc_pad, cudaStream_t st) {
+                        const void* Xq, int xq_is_f32, int64_t qc, int64_t qc_pad, double* mu_chunk, cudaStream_t st) {
   const int64_t np = w.np;
   prof_begin(kProfKstar, st);
   static const bool use_mma = getenv("BBO_KSTAR_NO_MMA") == nullptr;
@@ -2269,10 +2273,10 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
     const double* hyp = s.hyp;
     if (matern)
       k_kstar_umma<true><<<unsigned(grid), ku::THREADS, sm, st>>>(mapA, mapB, mapO, int(np), tiles, nbox, 3 * dk / 8,
-                                                                 s.h.d, hyp, t.alpha32, t.mu[buf]);
+                                                                 s.h.d, hyp, t.alpha32, mu_chunk);
     else
       k_kstar_umma<false><<<unsigned(grid), ku::THREADS, sm, st>>>(mapA, mapB, mapO, int(np), tiles, nbox, 3 * dk / 8,
-                                                                  s.h.d, hyp, t.alpha32, t.mu[buf]);
+                                                                  s.h.d, hyp, t.alpha32, mu_chunk);
   } else if (use_kstar_v3(s.h.d, np)) {
     const int ks = (s.h.d + 2 + 7) / 8;
     const bool matern = s.h.kind == BBO_KERNEL_MATERN52;
@@ -2285,7 +2289,7 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
     BBO_LAUNCH_CHECK();
 #define BBO_KSTAR_MMA3_L(KS_, G_, M_)                                                                           \
   k_kstar_mma3<KS_, G_, M_><<<unsigned(qc_pad / (8 * G_)), 256, Kstar3Cfg<KS_>::kSmem, st>>>(                   \
-      s.h, t.Bfrag, t.Xhi, np, s.hyp, t.alpha32, t.Ks[buf], t.mu[buf])
+      s.h, t.Bfrag, t.Xhi, np, s.hyp, t.alpha32, t.Ks[buf], mu_chunk)
 #define BBO_KSTAR_MMA3(KS_, G_)                                                                                 \
   case KS_: {                                                                                                   \
     static DeviceOnce attr_once;                                                                                \
@@ -2317,7 +2321,7 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
     const bool matern = s.h.kind == BBO_KERNEL_MATERN52;
 #define BBO_KSTAR_MMA2_L(T_, KS_, M_)                                                                          \
   k_kstar_mma2<T_, KS_, M_><<<grid, 256, sm, st>>>(s.h, static_cast<const T_*>(Xq), qc, t.Xhi, t.Xlo, np, s.hyp, \
-                                                   t.alpha32, t.Ks[buf], t.mu[buf])
+                                                   t.alpha32, t.Ks[buf], mu_chunk)
 #define BBO_KSTAR_MMA2(KS_)                                                                                    \
   case KS_: {                                                                                                  \
     const size_t sm = kstar_mma2_smem<KS_>();                                                                  \
@@ -2377,10 +2381,10 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
     }                                                                                                          \
     if (xq_is_f32)                                                                                             \
       k_kstar_mma<float, KS_><<<grid, 256, sm, st>>>(s.h, static_cast<const float*>(Xq), qc, t.Xhi, t.Xlo,      \
-                                                     t.bnorm, s.n, np, s.hyp, t.alpha32, t.Ks[buf], t.mu[buf]);  \
+                                                     t.bnorm, s.n, np, s.hyp, t.alpha32, t.Ks[buf], mu_chunk);  \
     else                                                                                                       \
       k_kstar_mma<double, KS_><<<grid, 256, sm, st>>>(s.h, static_cast<const double*>(Xq), qc, t.Xhi, t.Xlo,    \
-                                                      t.bnorm, s.n, np, s.hyp, t.alpha32, t.Ks[buf], t.mu[buf]); \
+                                                      t.bnorm, s.n, np, s.hyp, t.alpha32, t.Ks[buf], mu_chunk); \
   } break;
     switch (ks) {
       BBO_KSTAR_MMA(1)
@@ -2416,18 +2420,18 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
     if (xq_is_f32)
       k_kstar_f32_fast<float><<<unsigned(qc_pad / 128), 256, ksm, st>>>(s.h, static_cast<const float*>(Xq), qc, t.Xs,
                                                                      t.bnorm, s.n, np, s.hyp, t.alpha32, t.Ks[buf],
-                                                                     t.mu[buf]);
+                                                                     mu_chunk);
     else
       k_kstar_f32_fast<double><<<unsigned(qc_pad / 128), 256, ksm, st>>>(s.h, static_cast<const double*>(Xq), qc, t.Xs,
                                                                       t.bnorm, s.n, np, s.hyp, t.alpha32, t.Ks[buf],
-                                                                      t.mu[buf]);
+                                                                      mu_chunk);
   } else {
     if (xq_is_f32)
       k_kstar_f32<float><<<unsigned(qc_pad / 64), 256, 0, st>>>(s.h, static_cast<const float*>(Xq), qc, s.X, s.n, np,
-                                                               s.hyp, s.alpha, t.Ks[buf], t.mu[buf]);
+                                                               s.hyp, s.alpha, t.Ks[buf], mu_chunk);
     else
       k_kstar_f32<double><<<unsigned(qc_pad / 64), 256, 0, st>>>(s.h, static_cast<const double*>(Xq), qc, s.X, s.n,
-                                                                np, s.hyp, s.alpha, t.Ks[buf], t.mu[buf]);
+                                                                np, s.hyp, s.alpha, t.Ks[buf], mu_chunk);
   }
   BBO_LAUNCH_CHECK();
   prof_end(kProfKstar, st);
@@ -2608,43 +2612,92 @@ int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const vo
     BBO_CUDA_CHECK(cudaStreamWaitEvent(aux->ss, aux->entry, 0));
   }
   const int64_t nchunk = ceil_div(q, w.qp);
+  // BBO_TF32_TIMELINE=1 (debug aid): start / end of every K*, panel and selection of the call, in us after the first
+  // launch, on stderr (synchronises at the end of the call)
+  static const bool timeline = getenv("BBO_TF32_TIMELINE") != nullptr;
+  std::vector<cudaEvent_t> tl;
+  auto mark = [&](cudaStream_t sx) {
+    if (!timeline) return;
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, sx);
+    tl.push_back(e);
+  };
   auto chunk_len = [&](int64_t i) { return (q - i * w.qp < w.qp) ? q - i * w.qp : w.qp; };
   auto chunk_ptr = [&](int64_t i) { return static_cast<const char*>(Xq) + size_t(i) * w.qp * d * esz; };
   {
     const int64_t qc = chunk_len(0);
-    rc = launch_kstar(s, w, t, 0, chunk_ptr(0), xq_is_f32, qc, ceil_div(qc, 128) * 128, aux->sk);
+    mark(aux->sk);
+    rc = launch_kstar(s, w, t, 0, chunk_ptr(0), xq_is_f32, qc, ceil_div(qc, 128) * 128, t.mu[0], aux->sk);
     if (rc != BBO_OK) return rc;
+    mark(aux->sk);
     if (two_streams) BBO_CUDA_CHECK(cudaEventRecord(aux->kdone[0], aux->sk));
   }
   for (int64_t i = 0; i < nchunk; ++i) {
     const int buf = int(i & 1);
     if (i + 1 < nchunk) {
       const int nb = buf ^ 1;
-      if (two_streams && i >= 1) {   // chunk i-1 released buffer nb: panel (Ks) and selection (mu, partial sums)
-        BBO_CUDA_CHECK(cudaStreamWaitEvent(aux->sk, aux->pdone[nb], 0));
-        BBO_CUDA_CHECK(cudaStreamWaitEvent(aux->sk, aux->sdone[nb], 0));
-      }
+      // chunk i-1 released K* buffer nb when its panel finished.  mu is triple-buffered, so K*(i+1) never waits for
+      // the selection of chunk i-1 (small kernels that start when panel(i-1) ends, as this K* would like to);
+      // mu[(i+1) % 3] was last read by the selection of chunk i-2, finished a whole panel ago (sdone[buf] still holds
+      // that record here: chunk i's own is made further down).  Steady state (BBO_TF32_TIMELINE=1): panel(i) and
+      // K*(i+1) become ready together, the panel takes the SMs, K*(i+1) runs when it ends (~95 us), panel(i+1)
+      // follows 6 us later: a chunk costs panel + K*, selection runs beside the K*.
+      if (two_streams && i >= 1) BBO_CUDA_CHECK(cudaStreamWaitEvent(aux->sk, aux->pdone[nb], 0));
+      if (two_streams && i >= 2) BBO_CUDA_CHECK(cudaStreamWaitEvent(aux->sk, aux->sdone[buf], 0));
       const int64_t qn = chunk_len(i + 1);
-      rc = launch_kstar(s, w, t, nb, chunk_ptr(i + 1), xq_is_f32, qn, ceil_div(qn, 128) * 128, aux->sk);
+      mark(aux->sk);
+      rc = launch_kstar(s, w, t, nb, chunk_ptr(i + 1), xq_is_f32, qn, ceil_div(qn, 128) * 128, t.mu[(i + 1) % 3],
+                        aux->sk);
       if (rc != BBO_OK) return rc;
+      mark(aux->sk);
       if (two_streams) BBO_CUDA_CHECK(cudaEventRecord(aux->kdone[nb], aux->sk));
     }
     const int64_t qc = chunk_len(i);
-    if (two_streams) BBO_CUDA_CHECK(cudaStreamWaitEvent(st, aux->kdone[buf], 0));
+    if (two_streams) {
+      BBO_CUDA_CHECK(cudaStreamWaitEvent(st, aux->kdone[buf], 0));
+      // the partial-sum buffer `buf` was read by the selection of chunk i-2 (long finished)
+      if (i >= 2) BBO_CUDA_CHECK(cudaStreamWaitEvent(st, aux->sdone[buf], 0));
+    }
     int nsplit = 1;
     double* vpart = nullptr;
+    mark(st);
     rc = launch_panel(s, w, t, buf, ceil_div(qc, 128) * 128, w.vpart + int64_t(buf) * 4 * w.qp, &nsplit, &vpart, st);
     if (rc != BBO_OK) return rc;
+    mark(st);
     if (two_streams) {
       BBO_CUDA_CHECK(cudaEventRecord(aux->pdone[buf], st));
       BBO_CUDA_CHECK(cudaStreamWaitEvent(ssel, aux->pdone[buf], 0));
     }
-    rc = consume(i * w.qp, qc, t.mu[buf], nsplit, vpart, ssel);
+    mark(ssel);
+    rc = consume(i * w.qp, qc, t.mu[i % 3], nsplit, vpart, ssel);
     if (rc != BBO_OK) return rc;
+    mark(ssel);
     if (two_streams) BBO_CUDA_CHECK(cudaEventRecord(aux->sdone[buf], ssel));
   }
   if (two_streams) {   // the caller's stream sees the finished selection
     BBO_CUDA_CHECK(cudaStreamWaitEvent(st, aux->sdone[int((nchunk - 1) & 1)], 0));
+  }
+  if (timeline) {
+    // order of marks: K*(0) begin/end, then per chunk i: [K*(i+1) begin/end,] panel(i) begin/end, selection(i) begin/end
+    cudaDeviceSynchronize();
+    size_t m = 2;
+    for (int64_t i = 0; i < nchunk && i < 8; ++i) {
+      float kb = -1.f, ke = -1.f, pb = -1.f, pe = -1.f, sb = -1.f, se = -1.f;
+      if (i + 1 < nchunk) {
+        cudaEventElapsedTime(&kb, tl[0], tl[m]);
+        cudaEventElapsedTime(&ke, tl[0], tl[m + 1]);
+        m += 2;
+      }
+      cudaEventElapsedTime(&pb, tl[0], tl[m]);
+      cudaEventElapsedTime(&pe, tl[0], tl[m + 1]);
+      cudaEventElapsedTime(&sb, tl[0], tl[m + 2]);
+      cudaEventElapsedTime(&se, tl[0], tl[m + 3]);
+      m += 4;
+      fprintf(stderr, "tf32 timeline chunk %lld: panel %.1f -> %.1f us   K*(next) %.1f -> %.1f us   select %.1f -> %.1f us\n",
+              (long long)i, pb * 1e3f, pe * 1e3f, kb * 1e3f, ke * 1e3f, sb * 1e3f, se * 1e3f);
+    }
+    for (cudaEvent_t e : tl) cudaEventDestroy(e);
   }
   return BBO_OK;
 }
