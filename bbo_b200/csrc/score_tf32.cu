@@ -803,7 +803,8 @@ k_vnorm_tf32_2sm(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 // dealt by list scheduling: every item goes to the CTA pair with the least work so far (lowest index on ties).
 // That is what a run-time work queue would do under this cost model, without any in-kernel hand-over.  The K*
 // strip of a tile pair (256 x np floats) is read by all of its row pairs while it is still in L2, instead of
-// 4.5 times from HBM.  sched[c * maxj + j] = 64 tp + r, -1 terminated.
+// 4.5 times from HBM.  sched[c * maxj + j] = 64 tp + r, -1 terminated; a list holds at most maxj - 1 items and a full
+// list is passed over (nc * (maxj - 1) >= ntp * nrp is the caller's side of the contract).
 // ------------------------------------------------------------------------------------------
 __global__ void k_panel_schedule(int ntp, int nrp, int nc, int gs, int maxj, int* __restrict__ sched) {
   const int lane = threadIdx.x;
@@ -817,7 +818,7 @@ __global__ void k_panel_schedule(int ntp, int nrp, int nc, int gs, int maxj, int
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
           const int c = lane + 32 * i;
-          if (c < nc && load[i] < best) {
+          if (c < nc && cnt[i] < maxj - 1 && load[i] < best) {   // a full list takes no more items
             best = load[i];
             bc = c;
           }
@@ -835,7 +836,7 @@ __global__ void k_panel_schedule(int ntp, int nrp, int nc, int gs, int maxj, int
 #pragma unroll
           for (int ii = 0; ii < 3; ++ii)
             if (ii == i) {
-              if (cnt[ii] < maxj - 1) sched[int64_t(bc) * maxj + cnt[ii]] = tp * 64 + r;
+              sched[int64_t(bc) * maxj + cnt[ii]] = tp * 64 + r;
               cnt[ii] += 1;
               load[ii] += 4 * (r + 1) + 1;
             }
@@ -2496,7 +2497,9 @@ static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
     static const bool no_persist = getenv("BBO_TF32_NO_PERSIST") != nullptr;
     const int ntp = int(tiles / 2), nrp = int((nblk + 1) / 2);
     const int nc = ntp < sm_count() / 2 ? ntp : sm_count() / 2;
-    const int maxj = (ntp * nrp + nc - 1) / nc * 2 + 4;
+    // list capacity: four times the mean item count (the lists hold ntp * nrp items in total, so with full lists
+    // skipped by the scheduler every item finds a place)
+    const int maxj = (ntp * nrp + nc - 1) / nc * 4 + 8;
     // The persistent form trades the lock-step walk over the row pairs (which keeps the L^-1 blocks in flight few)
     // for K* strip reuse: it needs the whole TF32 L^-1 resident in L2 next to the strips (n = 4096: 67 of 126 MB).
     // At n = 8192 (268 MB) it was 9 % slower than the lock-step form, which therefore keeps the large problems.

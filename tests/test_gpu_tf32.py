@@ -74,10 +74,11 @@ def test_tf32_matches_fp64_mode_statistically(cuda_device):
     assert np.abs(np_(mu32 - mu64)).max() < 1e-3
 
 
-def test_tf32_earlier_kstar_producers_still_agree(cuda_device):
+def test_tf32_alternative_kernels_agree(cuda_device):
     """The mma.sync K* producers stay selectable (BBO_KSTAR_NO_UMMA=1: second / third form); they must give the
-    selection and (to TF32 accuracy) the scores of the default tcgen05 producer.  The switch is read once per
-    process, hence the subprocess."""
+    selection and (to TF32 accuracy) the scores of the default tcgen05 producer.  The lock-step panel
+    (BBO_TF32_NO_PERSIST=1) must give the bits of the persistent one.  The switches are read once per process,
+    hence the subprocesses."""
     import os, subprocess, sys, json
     code = r"""
 import json, numpy as np, torch, sys
@@ -95,7 +96,7 @@ for n, d, kind in [(2100, 20, O.RBF), (600, 24, O.MATERN52)]:
 print("RESULT" + json.dumps(out))
 """ % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
     res = {}
-    for tag, extra in [("umma", {}), ("mma", {"BBO_KSTAR_NO_UMMA": "1"})]:
+    for tag, extra in [("umma", {}), ("mma", {"BBO_KSTAR_NO_UMMA": "1"}), ("lockstep", {"BBO_TF32_NO_PERSIST": "1"})]:
         env = dict(os.environ, **extra)
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr[-2000:]
@@ -106,3 +107,7 @@ print("RESULT" + json.dumps(out))
         sm, im = res["mma"][key]
         assert len(set(iu) & set(im)) >= 7
         assert np.allclose(su, sm, rtol=2e-3, atol=1e-6)
+        # the persistent panel (work lists, one partial-sum slot per row block) and the lock-step panel (four slots)
+        # add the same numbers in the same association: bit-identical scores and indices
+        sl, il = res["lockstep"][key]
+        assert il == iu and sl == su
