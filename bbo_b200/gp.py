@@ -177,18 +177,28 @@ class CudaGP(Surrogate):
         g_constant) -- float64 device tensors."""
         with torch.cuda.device(self._device):
             h = self._hyper()
-            hyp = self._hyp_from_modules()
             ws = self._fit_ws()
-            value = torch.empty(1, dtype=_F64, device=self._device)
-            grad = torch.empty(self.d + 2, dtype=_F64, device=self._device)
-            info = torch.zeros(1, dtype=torch.int32, device=self._device)
+            # the library replays the whole iteration as a CUDA graph while it is called with the same buffers, so
+            # the hyper-parameters, outputs and the info word live in buffers kept with the workspace; the caller
+            # gets copies
+            bufs = self._ws.get("vg")
+            if bufs is None or bufs[0].numel() != 2 * self.d + 2:
+                bufs = (torch.empty(2 * self.d + 2, dtype=_F64, device=self._device),
+                        torch.empty(1, dtype=_F64, device=self._device),
+                        torch.empty(self.d + 2, dtype=_F64, device=self._device),
+                        torch.zeros(1, dtype=torch.int32, device=self._device))
+                self._ws["vg"] = bufs
+            hyp, value_b, grad_b, info = bufs
+            hyp.copy_(self._hyp_from_modules())
+            info.zero_()
             _lib.check(self._lib.bbo_gp_fit_value_grad(
-                C.byref(h), self.n, 1, _lib.ptr(self._X), _lib.ptr(self._Y), _lib.ptr(hyp), _lib.ptr(value),
-                _lib.ptr(grad), _lib.ptr(info), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(self._device)),
+                C.byref(h), self.n, 1, _lib.ptr(self._X), _lib.ptr(self._Y), _lib.ptr(hyp), _lib.ptr(value_b),
+                _lib.ptr(grad_b), _lib.ptr(info), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(self._device)),
                 "bbo_gp_fit_value_grad")
             i = int(info.item())
             if i != 0:
                 _raise_not_pd(i)
+            value, grad = value_b.clone(), grad_b.clone()
         th = self._theta
         raw_ls = th.raw_ls.detach().to(device=self._device, dtype=_F64)
         sg = torch.where(raw_ls > 20.0, torch.ones_like(raw_ls), torch.sigmoid(raw_ls))
