@@ -2496,7 +2496,10 @@ static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
     static const int shrink = getenv("BBO_TF32_FULL_DIAG") == nullptr ? 1 : 0;
     static const bool no_persist = getenv("BBO_TF32_NO_PERSIST") != nullptr;
     const int ntp = int(tiles / 2), nrp = int((nblk + 1) / 2);
-    const int nc = ntp < sm_count() / 2 ? ntp : sm_count() / 2;
+    // CTA pairs: one per SM pair, or one per item when the chunk has fewer items than that (a small pool spreads the
+    // row pairs of its few tile pairs over the chip)
+    const int nitems = ntp * nrp;
+    const int nc = nitems < sm_count() / 2 ? nitems : sm_count() / 2;
     // list capacity: four times the mean item count (the lists hold ntp * nrp items in total, so with full lists
     // skipped by the scheduler every item finds a place)
     const int maxj = (ntp * nrp + nc - 1) / nc * 4 + 8;
