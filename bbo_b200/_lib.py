@@ -18,7 +18,9 @@ STATUS_NAMES = {0: "BBO_OK", 1: "BBO_ERR_BAD_SHAPE", 2: "BBO_ERR_BAD_ARG", 3: "B
                 4: "BBO_ERR_CUDA", 5: "BBO_ERR_NOT_PD", 6: "BBO_ERR_NAN"}
 KERNEL_RBF, KERNEL_MATERN52 = 0, 1
 ACQ_EI, ACQ_UCB, ACQ_PI = 0, 1, 2
-PREC_FP64, PREC_TF32 = 0, 1
+PREC_FP64, PREC_TF32, PREC_TF32_REFINE = 0, 1, 2
+PRECISIONS = {"fp64": PREC_FP64, "tf32": PREC_TF32, "tf32+refine": PREC_TF32_REFINE}
+REFINE_KMAX = 32
 ROW_ALIGN = 128
 TOPK_MAX = 128
 APPEND_MAX = 32
@@ -77,6 +79,8 @@ SIGNATURES = {
                                     _P, _P, _P, _P, _P, _SZ, _I64, _I32, _P]),
     "bbo_gp_score_pool_host": (C.c_int, [C.POINTER(GpState), C.POINTER(Acq), _I32, _P, _I32, _I64, _I64, _I32,
                                          _P, _P, _P, _P, _P, _P, _SZ, _I64, _P]),
+    "bbo_refine_shortlist": (_I32, [_I32]),
+    "bbo_gp_refine_info": (C.c_int, [_P, _SZ, _I64, _I64, _I64, C.POINTER(C.c_double), _P]),
     "bbo_gp_score_batched_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I64]),
     "bbo_gp_score_pool_batched": (C.c_int, [C.POINTER(GpHyper), _I64, _I64, _P, _P, _P, _P, _P, _P, _I64, _I32, _P, _P,
                                             _P, _SZ, _P]),

@@ -1,15 +1,30 @@
 """Plug-in interfaces of the hot path.
 
-When the reference package ``bbo`` is importable its own ABCs are re-exported, so the
-classes in this package *are* ``bbo`` surrogates / acquisition functions / optimizers.
-Otherwise (e.g. on the GPU box, where the reference is absent) structurally identical
-mirrors are defined:
+When the reference package ``bbo`` is importable (already on ``sys.path``, or under ``$BBO_REFERENCE``) its
+own ABCs are the base classes, so the classes in this package *are* ``bbo`` surrogates / acquisition
+functions / optimizers.  Otherwise structurally identical mirrors are defined:
 
   Surrogate               bbo/algorithms/abstractions.py:78-85
   AcquisitionFunction     bbo/algorithms/designers/bo/acquisitions.py:7-10
   GradientFreeOptimizer   bbo/algorithms/optimizers/base.py:8-18
+
+If ``bbo`` only becomes importable AFTER this package was imported (the mirrors are then the bases),
+``adopt_reference_abcs`` registers the classes as virtual subclasses of the reference ABCs, so that
+``BODesigner``'s ``instance_of(GradientFreeOptimizer)`` validator (bo.py:64) accepts them either way.
+It is called from the constructors of ``PoolOptimizer`` / ``CudaGP`` / the acquisition classes.
 """
 import abc
+import os
+import sys
+
+
+def _reference_on_path() -> None:
+    p = os.environ.get("BBO_REFERENCE")
+    if p and os.path.isdir(os.path.join(p, "bbo")) and p not in sys.path:
+        sys.path.insert(0, p)
+
+
+_reference_on_path()
 
 try:  # pragma: no cover - depends on the environment
     from bbo.algorithms.abstractions import Surrogate  # type: ignore
@@ -39,3 +54,20 @@ except Exception:  # noqa: BLE001
         @abc.abstractmethod
         def __call__(self, mu, stddev):
             pass
+
+
+_REFERENCE_ABCS = {
+    "Surrogate": ("bbo.algorithms.abstractions", "Surrogate"),
+    "GradientFreeOptimizer": ("bbo.algorithms.optimizers.base", "GradientFreeOptimizer"),
+    "AcquisitionFunction": ("bbo.algorithms.designers.bo.acquisitions", "AcquisitionFunction"),
+}
+
+
+def adopt_reference_abcs(cls, role: str) -> None:
+    """Register ``cls`` with the reference's ABC for ``role`` if that module is loaded and ``cls`` does not
+    already derive from it (import-order independence; no import is triggered here)."""
+    modname, attr = _REFERENCE_ABCS[role]
+    mod = sys.modules.get(modname)
+    ref = getattr(mod, attr, None) if mod is not None else None
+    if ref is not None and isinstance(ref, abc.ABCMeta) and not issubclass(cls, ref):
+        ref.register(cls)

@@ -12,7 +12,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from .abstractions import AcquisitionFunction
+from .abstractions import AcquisitionFunction, adopt_reference_abcs
 
 
 class _DeviceAcq(AcquisitionFunction):
@@ -43,6 +43,7 @@ class EI(_DeviceAcq):
     kind = _lib.ACQ_EI
 
     def __init__(self, best_f, eps: float = 1e-6):
+        adopt_reference_abcs(type(self), "AcquisitionFunction")
         self._best_f = float(best_f)
         self._eps = float(eps)
 
@@ -55,6 +56,7 @@ class UCB(_DeviceAcq):
     kind = _lib.ACQ_UCB
 
     def __init__(self, beta: float = 1.8):
+        adopt_reference_abcs(type(self), "AcquisitionFunction")
         self.beta = float(beta)
 
     def descriptor(self):
@@ -66,6 +68,7 @@ class PI(_DeviceAcq):
     kind = _lib.ACQ_PI
 
     def __init__(self, best_f, eps: float = 1e-6):
+        adopt_reference_abcs(type(self), "AcquisitionFunction")
         self._best_f = float(best_f)
         self._eps = float(eps)
 

@@ -3,17 +3,65 @@
 Branin2D and Ackley follow bbo/benchmarks/experimenters/synthetic.py:47-93 (same constants,
 bounds, optima); Rastrigin and Levy are named by BASELINE.json configs but absent from the
 reference and follow the standard sfu.ca/~ssurjano definitions.  All are
-MINIMIZE problems; `unit_to_domain` maps the GP's [0,1]^d features to the native box.
+MINIMIZE problems (``goal``); `unit_to_domain` maps the GP's [0,1]^d features to the native box.
+When the reference is importable every class here IS a ``bbo`` ``SyntheticFunction``, so
+``SyntheticExperimenter(Rastrigin(50))`` / ``SyntheticExperimenter(Levy(100))`` work unchanged.
 """
 from __future__ import annotations
 
 import numpy as np
 
 
-class SyntheticFunction:
+try:  # the reference's own base class and goal enum when `bbo` is importable (benchmarks/experimenters/synthetic.py:13-24)
+    from bbo.benchmarks.experimenters.synthetic import SyntheticFunction as _RefSyntheticFunction  # type: ignore
+    from bbo.shared.base_study_config import ObjectiveMetricGoal  # type: ignore
+    HAVE_BBO = True
+except Exception:  # noqa: BLE001
+    import abc
+    import enum
+    HAVE_BBO = False
+
+    class ObjectiveMetricGoal(enum.Enum):     # shared/base_study_config.py:24-34
+        MAXIMIZE = 1
+        MINIMIZE = 2
+
+        @property
+        def is_maximize(self) -> bool:
+            return self == self.MAXIMIZE
+
+        @property
+        def is_minimize(self) -> bool:
+            return self == self.MINIMIZE
+
+    class _RefSyntheticFunction(abc.ABC):     # synthetic.py:13-24
+        num_objectives: int = 1
+
+        @abc.abstractmethod
+        def __call__(self, X):
+            pass
+
+
+class SyntheticFunction(_RefSyntheticFunction):
+    """A reference ``SyntheticFunction`` (usable with ``SyntheticExperimenter(func)``, synthetic.py:27-45)
+    plus the unit-cube helpers the tensor path uses."""
     dim: int
     bounds: list
+    goal = ObjectiveMetricGoal.MINIMIZE
     optimal_value: float
+    optimal_points = None
+
+    def __new__(cls, *args, **kwargs):
+        # import-order independence: if `bbo` was imported after this module, the mirror above is the base class;
+        # register with the reference's ABC so SyntheticExperimenter's instance_of validator accepts the instance
+        import sys
+        mod = sys.modules.get("bbo.benchmarks.experimenters.synthetic")
+        ref = getattr(mod, "SyntheticFunction", None) if mod is not None else None
+        if ref is not None and not issubclass(cls, ref):
+            ref.register(cls)
+            goal = getattr(sys.modules.get("bbo.shared.base_study_config"), "ObjectiveMetricGoal", None)
+            if goal is not None and not isinstance(cls.goal, goal):
+                cls.goal = goal[cls.goal.name]
+        return super().__new__(cls)
 
     def unit_to_domain(self, U: np.ndarray) -> np.ndarray:
         lb = np.array([b[0] for b in self.bounds], dtype=np.float64)

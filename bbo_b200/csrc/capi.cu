@@ -1,5 +1,6 @@
 // extern "C" surface of libbbo_b200.so (see include/bbo_b200.h for the contract).
 #include <atomic>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -25,7 +26,9 @@ struct Retired {
   cudaEvent_t done;
 };
 static std::vector<Retired> g_retired;
+static std::mutex g_state_mutex;   // guards the library-global caches below (g_retired, g_prof, HostAux)
 void retire_graph(cudaGraphExec_t exec, cudaGraph_t graph, cudaStream_t st) {
+  std::lock_guard<std::mutex> lock(g_state_mutex);
   for (size_t i = 0; i < g_retired.size();) {
     if (cudaEventQuery(g_retired[i].done) == cudaSuccess) {
       cudaGraphExecDestroy(g_retired[i].exec);
@@ -65,12 +68,14 @@ static cudaEvent_t prof_event(int tag) {
 }
 void prof_begin(int tag, cudaStream_t st) {
   if (!g_prof.enabled) return;
+  std::lock_guard<std::mutex> lock(g_state_mutex);
   if (g_prof.used[tag] + 2 > kProfMaxEvents) return;
   cudaEvent_t e = prof_event(tag);
   if (e) cudaEventRecord(e, st);
 }
 void prof_end(int tag, cudaStream_t st) {
   if (!g_prof.enabled) return;
+  std::lock_guard<std::mutex> lock(g_state_mutex);
   if ((g_prof.used[tag] & 1) == 0) return;  // no matching begin
   cudaEvent_t e = prof_event(tag);
   if (e) cudaEventRecord(e, st);
@@ -89,12 +94,14 @@ extern "C" {
 int bbo_version(void) { return 100; }
 int64_t bbo_launch_count(void) { return g_launches.load(); }
 void bbo_profile_enable(int32_t on) {
+  std::lock_guard<std::mutex> lock(g_state_mutex);
   g_prof.enabled = on != 0;
   for (int t = 0; t < kProfTags; ++t) g_prof.used[t] = 0;
 }
 int bbo_profile_read(int32_t tag, int64_t* regions, double* total_ms) {
   if (tag < 0 || tag >= kProfTags || !regions || !total_ms) return BBO_ERR_BAD_ARG;
   BBO_CUDA_CHECK(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lock(g_state_mutex);
   double tot = 0.0;
   int64_t n = 0;
   for (size_t i = 0; i + 1 < g_prof.used[tag]; i += 2) {
@@ -274,6 +281,9 @@ int bbo_gp_score_pool_host(const bbo_gp_state* st, const bbo_acq* acq, int32_t p
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return BBO_ERR_BAD_ARG;
   HostAux& ha = g_host_aux[dev];
+  // one host-pool call per device at a time: the staging hand-over events are per device
+  static std::mutex g_host_mutex[64];
+  std::lock_guard<std::mutex> host_lock(g_host_mutex[dev]);
   // one staging buffer = BBO_HOST_STAGE_CHUNKS scoring chunks, so that the K*/panel pipeline inside
   // gp_score_pool has several chunks to overlap
   const int64_t qp = BBO_HOST_STAGE_CHUNKS * (q_chunk < 128 ? 128 : (q_chunk + 127) / 128 * 128);
@@ -320,12 +330,21 @@ int bbo_gp_score_pool_host(const bbo_gp_state* st, const bbo_acq* acq, int32_t p
                                    cudaMemcpyHostToDevice, copy));
     BBO_HOST_CHECK(cudaEventRecord(ready[buf], copy));
     BBO_HOST_CHECK(cudaStreamWaitEvent(cs, ready[buf], 0));
+    // BBO_PREC_TF32_REFINE: every buffer only extends the short-list (its rows are kept in the workspace);
+    // the float64 re-score runs once, after the last buffer
+    const int rflags = kRefineDefer | (ci > 0 ? kRefineContinue : 0) | ((ci & 1) ? kRefineParity : 0);
     rc = gp_score_pool(*st, *acq, precision, dst, xq_is_f32, qc, index_offset + c0, k, topk_score_dev,
                        topk_index_dev, nullptr, nullptr, nullptr, nullptr, workspace_dev, workspace_bytes, q_chunk,
-                       ci > 0, cs);
+                       ci > 0, cs, rflags);
     if (rc != BBO_OK) { cudaStreamSynchronize(copy); return rc; }
     BBO_HOST_CHECK(cudaEventRecord(freed[buf], cs));
     c0 += qc;
+  }
+  if (precision == BBO_PREC_TF32_REFINE && q > 0) {
+    rc = gp_score_pool(*st, *acq, precision, staging_dev, xq_is_f32, 0, index_offset + q, k, topk_score_dev,
+                       topk_index_dev, nullptr, nullptr, nullptr, nullptr, workspace_dev, workspace_bytes, q_chunk,
+                       false, cs, kRefineContinue | ((ci & 1) ? kRefineParity : 0));
+    if (rc != BBO_OK) { cudaStreamSynchronize(copy); return rc; }
   }
   BBO_HOST_CHECK(cudaMemcpyAsync(topk_score_host, topk_score_dev, size_t(k) * sizeof(double),
                                  cudaMemcpyDeviceToHost, cs));
@@ -335,6 +354,13 @@ int bbo_gp_score_pool_host(const bbo_gp_state* st, const bbo_acq* acq, int32_t p
   BBO_HOST_CHECK(cudaStreamSynchronize(copy));
 #undef BBO_HOST_CHECK
   return BBO_OK;
+}
+
+int32_t bbo_refine_shortlist(int32_t k) { return refine_shortlist_len(k); }
+int bbo_gp_refine_info(const void* workspace_dev, size_t workspace_bytes, int64_t n, int64_t d, int64_t q_chunk,
+                       double* info_host, void* stream) {
+  if (!workspace_dev || !info_host || n < 1 || d < 1 || q_chunk < 1) return BBO_ERR_BAD_ARG;
+  return refine_info(workspace_dev, workspace_bytes, n, d, q_chunk, info_host, S(stream));
 }
 
 size_t bbo_gp_score_batched_workspace_bytes(int64_t n, int64_t d, int64_t batch, int64_t q) {

@@ -32,6 +32,7 @@ struct GemmCfg {
 
 using Cfg128x64 = GemmCfg<128, 64, 32, 32>;  // 8 warps, 64 accumulator registers / thread
 using Cfg64x64 = GemmCfg<64, 64, 32, 32>;    // 4 warps; every block boundary is 64-aligned
+using Cfg64x32 = GemmCfg<64, 32, 32, 16>;    // 4 warps; short-list re-scoring (many small CTAs)
 
 template <class Cfg>
 struct Acc {

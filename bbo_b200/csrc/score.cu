@@ -485,15 +485,18 @@ static int pick_nsplit(int64_t /*qc_pad*/, int64_t np) {
   return int(want);
 }
 
+static size_t refine_bytes(int64_t np, int64_t d);
 size_t ScoreWorkspace::bytes(int64_t n, int64_t d, int64_t q_chunk, int precision, bool want_full) {
   const int64_t np = padded(n), qp = round_chunk(q_chunk);
   const int64_t nblk = ceil_div(qp, kSeg);
-  const size_t ks = (precision == BBO_PREC_TF32 && !want_full) ? 0 : size_t(qp) * np;   // TF32 keeps K* in float32
+  const bool tf32 = precision != BBO_PREC_FP64;
+  const size_t ks = (tf32 && !want_full) ? 0 : size_t(qp) * np;   // TF32 keeps K* in float32
   size_t doubles = ks * (want_full ? 2 : 1)  // Ks (+V)
                    + size_t(kMaxSplit) * qp + 2 * size_t(qp)  // vpart, mu, score
-                   + 2 * size_t(BBO_TOPK_MAX) * (nblk + 1) * 2;  // two (score,index) ping-pong lists
+                   + 2 * (size_t(BBO_TOPK_MAX) * (nblk + 1) + 256) * 2;  // two (score,index) ping-pong lists
   size_t extra = 0;
-  if (precision == BBO_PREC_TF32) extra = score_tf32_extra_bytes(n, d, qp);
+  if (tf32) extra = score_tf32_extra_bytes(n, d, qp);
+  if (precision == BBO_PREC_TF32_REFINE) extra += refine_bytes(np, d);
   return doubles * sizeof(double) + extra + 512;
 }
 
@@ -505,7 +508,8 @@ int ScoreWorkspace::bind(void* ws, size_t ws_bytes, int64_t n, int64_t d, int64_
   uintptr_t p = (reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255);
   double* q = reinterpret_cast<double*>(p);
   Ks = q;
-  if (!(precision == BBO_PREC_TF32 && !want_full)) q += size_t(qp) * np;
+  const bool tf32m = precision != BBO_PREC_FP64;
+  if (!(tf32m && !want_full)) q += size_t(qp) * np;
   V = want_full ? q : nullptr;
   if (want_full) q += size_t(qp) * np;
   vpart = q;
@@ -515,7 +519,7 @@ int ScoreWorkspace::bind(void* ws, size_t ws_bytes, int64_t n, int64_t d, int64_
   score = q;
   q += qp;
   const int64_t nblk = ceil_div(qp, kSeg);
-  list_len = int64_t(BBO_TOPK_MAX) * (nblk + 1);
+  list_len = int64_t(BBO_TOPK_MAX) * (nblk + 1) + 256;
   la_s = q;
   q += list_len;
   lb_s = q;
@@ -525,7 +529,222 @@ int ScoreWorkspace::bind(void* ws, size_t ws_bytes, int64_t n, int64_t d, int64_
   lb_i = reinterpret_cast<int64_t*>(q);
   q += list_len;
   tf32 = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(q) + 255) & ~uintptr_t(255));
+  refine = nullptr;
+  if (precision == BBO_PREC_TF32_REFINE)
+    refine = static_cast<char*>(tf32) + ((score_tf32_extra_bytes(n, d, qp) + 255) & ~size_t(255));
   return BBO_OK;
+}
+
+
+// ==========================================================================================
+// BBO_PREC_TF32_REFINE: short-list by TF32 score, float64 re-score of the short-list
+// ==========================================================================================
+constexpr int kRefineRows = 256;   // capacity of the short-list (refine_shortlist_len(k) <= this)
+int refine_shortlist_len(int k) {
+  int m = 8 * k;
+  if (m < 64) m = 64;
+  if (m > kRefineRows) m = kRefineRows;
+  return m;
+}
+static int refine_kseg(int k) { return 2 * k; }   // entries kept per 2048-candidate segment
+
+struct RefineScratch {
+  double* sh_s;        // (256) short-list TF32 scores, descending
+  int64_t* sh_i;       // (256) their global indices (-1 = empty slot)
+  double* bound;       // (1)   max TF32 score dropped at the segment level
+  double* info;        // (4)   see bbo_gp_refine_info
+  double* Xg[2];       // (256, d) rows of the short-listed candidates, ping-pong across continued calls
+  int64_t* gi[2];      // (256) indices the rows of Xg[p] belong to
+  double* tf_s;        // (256) TF32 scores in the order of the gathered rows
+  double* Ks;          // (256, np) float64 cross-covariance of the short-list
+  double* mu;          // (256)
+  double* part;        // (np/32, 256) |v|^2 partial sums, one slot per 32-row block of L^-1
+  double* la_s;        // (512) selection list: running top-k, then the re-scored short-list
+  int64_t* la_i;
+};
+static size_t refine_bytes(int64_t np, int64_t d) {
+  const size_t R = kRefineRows;
+  size_t doubles = R + R + 8 + 8 + 2 * R * size_t(d) + 2 * R + R + R * size_t(np) + R + size_t(np / 32) * R + 4 * R;
+  return doubles * sizeof(double) + 1024;
+}
+static RefineScratch carve_refine(void* base, int64_t np, int64_t d) {
+  RefineScratch r;
+  const size_t R = kRefineRows;
+  double* q = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(base) + 255) & ~uintptr_t(255));
+  r.sh_s = q;  q += R;
+  r.sh_i = reinterpret_cast<int64_t*>(q);  q += R;
+  r.bound = q;  q += 8;
+  r.info = q;  q += 8;
+  for (int p = 0; p < 2; ++p) { r.Xg[p] = q;  q += R * size_t(d); }
+  for (int p = 0; p < 2; ++p) { r.gi[p] = reinterpret_cast<int64_t*>(q);  q += R; }
+  r.tf_s = q;  q += R;
+  r.Ks = q;  q += R * size_t(np);
+  r.mu = q;  q += R;
+  r.part = q;  q += size_t(np / 32) * R;
+  r.la_s = q;  q += 2 * R;
+  r.la_i = reinterpret_cast<int64_t*>(q);  q += 2 * R;
+  return r;
+}
+
+__global__ void k_refine_init(double* sh_s, int64_t* sh_i, double* bound, int m) {
+  const int t = threadIdx.x;
+  if (t < m) {
+    sh_s[t] = -INFINITY;
+    sh_i[t] = -1;
+  }
+  if (t == 0) *bound = -INFINITY;
+}
+
+// bound = max(bound, the kseg-th (last kept) TF32 score of every segment list): everything a segment dropped
+// scored no more than that.  Lists with fewer than kseg valid entries end in (-inf, -1): nothing was dropped.
+__global__ void __launch_bounds__(256)
+k_refine_bound(const double* __restrict__ seg_s, const int64_t* __restrict__ seg_i, int nb, int kseg,
+               double* __restrict__ bound) {
+  __shared__ double red[256];
+  double v = -INFINITY;
+  for (int b = threadIdx.x; b < nb; b += 256) {
+    const int64_t p = int64_t(b) * kseg + kseg - 1;
+    if (seg_i[p] >= 0) v = fmax(v, seg_s[p]);
+  }
+  red[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *bound = fmax(*bound, red[0]);
+}
+
+// Rows of the short-listed candidates -> Xg_new (float64), in short-list order.  A candidate of this call's pool
+// [lo, lo+q) is read from Xq; one carried over from an earlier (continued) call is found by index in the previous
+// row buffer.  One block, 256 threads.
+template <typename T1>
+__global__ void __launch_bounds__(256)
+k_refine_gather(const T1* __restrict__ Xq, int64_t lo, int64_t q, int d, const double* __restrict__ sh_s,
+                const int64_t* __restrict__ sh_i, int m, const double* __restrict__ Xg_prev,
+                const int64_t* __restrict__ gi_prev, double* __restrict__ Xg_new, int64_t* __restrict__ gi_new,
+                double* __restrict__ tf_s) {
+  __shared__ int src;
+  for (int j = 0; j < kRefineRows; ++j) {
+    const int64_t ix = j < m ? sh_i[j] : -1;
+    const bool local = ix >= lo && ix < lo + q;
+    if (threadIdx.x == 0) src = -1;
+    __syncthreads();
+    if (ix >= 0 && !local && gi_prev != nullptr && gi_prev[threadIdx.x] == ix) src = threadIdx.x;
+    __syncthreads();
+    const int sp = src;
+    int64_t keep = ix;
+    for (int c = threadIdx.x; c < d; c += 256) {
+      double v = 0.0;
+      if (ix >= 0 && local) v = static_cast<double>(Xq[(ix - lo) * d + c]);
+      else if (ix >= 0 && sp >= 0) v = Xg_prev[int64_t(sp) * d + c];
+      Xg_new[int64_t(j) * d + c] = v;
+    }
+    if (ix >= 0 && !local && sp < 0) keep = -1;   // cannot happen (every carried index is in gi_prev); drop it if so
+    if (threadIdx.x == 0) {
+      gi_new[j] = keep;
+      tf_s[j] = j < m ? sh_s[j] : -INFINITY;
+    }
+    __syncthreads();
+  }
+}
+
+// part[it, c] = sum over the 32 rows i of block `it` of (sum_{j <= i} Ks[c,j] Linv[i,j])^2.
+// grid (np/32, rows/64), Cfg64x32: many small CTAs so that a 64..256-candidate short-list still uses the chip.
+__global__ void __launch_bounds__(Cfg64x32::THREADS)
+k_refine_vnorm(const double* __restrict__ Ks, const double* __restrict__ Linv, int64_t np, double* __restrict__ part) {
+  using Cfg = Cfg64x32;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ double red[Cfg::BM][Cfg::WARPS_N];
+  const int it = blockIdx.x;
+  const int64_t c0 = int64_t(blockIdx.y) * Cfg::BM;
+  Acc<Cfg> acc;
+  acc.zero();
+  gemm_nt_mainloop<Cfg>(Ks + c0 * np, np, Linv + int64_t(it) * Cfg::BN * np, np, 0, (it + 1) * Cfg::BN, acc, smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = warp / Cfg::WARPS_N, wn = warp % Cfg::WARPS_N;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int i = 0; i < Cfg::MF; ++i) {
+    double v = 0.0;
+#pragma unroll
+    for (int j = 0; j < Cfg::NF; ++j) {
+      v = fma(acc.v[i][j][0], acc.v[i][j][0], v);
+      v = fma(acc.v[i][j][1], acc.v[i][j][1], v);
+    }
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (t == 0) red[wm * Cfg::WM + i * 8 + g][wn] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < Cfg::BM) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < Cfg::WARPS_N; ++w) v += red[threadIdx.x][w];
+    part[int64_t(it) * kRefineRows + c0 + threadIdx.x] = v;
+  }
+}
+
+// float64 acquisition of the re-scored short-list + the selection list [running top-k | short-list] + evidence.
+__global__ void __launch_bounds__(kRefineRows)
+k_refine_acq(bbo_gp_hyper h, bbo_acq a, const double* __restrict__ hyp, const double* __restrict__ mu,
+             const double* __restrict__ part, int nblk, const int64_t* __restrict__ gi,
+             const double* __restrict__ tf_s, int m, int k, int keep_running, const double* __restrict__ run_s,
+             const int64_t* __restrict__ run_i, double* __restrict__ la_s, int64_t* __restrict__ la_i,
+             double* __restrict__ info, int32_t* __restrict__ nan_count) {
+  __shared__ double red[kRefineRows];
+  __shared__ int cnt[kRefineRows];
+  const int c = threadIdx.x;
+  const double eps = h.kind == BBO_KERNEL_MATERN52 ? h.pairwise_eps : 0.0;
+  const double kxx = hyp[2 * h.d] * kernel_from_s(h.kind, double(h.d) * eps * eps);
+  double err = 0.0;
+  int valid = 0;
+  if (c < m) {
+    double vn = 0.0;
+    for (int b = 0; b < nblk; ++b) vn += part[int64_t(b) * kRefineRows + c];
+    const double var = kxx - vn + h.noise;
+    double sc = acq_value<double>(a, mu[c], sqrt(var));
+    int64_t ix = gi[c];
+    if (ix >= 0 && sc != sc) {
+      ix = -1;
+      if (nan_count) atomicAdd(nan_count, 1);
+    }
+    if (ix < 0) sc = -INFINITY;
+    else {
+      valid = 1;
+      const double e = fabs(sc - tf_s[c]);
+      if (e == e && e < INFINITY) err = e;
+    }
+    la_s[k + c] = sc;
+    la_i[k + c] = ix;
+  }
+  if (c < k) {
+    la_s[c] = keep_running ? run_s[c] : -INFINITY;
+    la_i[c] = keep_running ? run_i[c] : -1;
+  }
+  red[c] = err;
+  cnt[c] = valid;
+  __syncthreads();
+  for (int o = kRefineRows / 2; o > 0; o >>= 1) {
+    if (c < o) {
+      red[c] = fmax(red[c], red[c + o]);
+      cnt[c] += cnt[c + o];
+    }
+    __syncthreads();
+  }
+  if (c == 0) {
+    info[2] = red[0];
+    info[3] = double(cnt[0]);
+  }
+}
+
+__global__ void k_refine_info(const double* __restrict__ topk_s, int k, const double* __restrict__ sh_s,
+                              const int64_t* __restrict__ sh_i, int m, const double* __restrict__ bound,
+                              double* __restrict__ info) {
+  info[0] = topk_s[k - 1];
+  double b = *bound;
+  if (sh_i[m - 1] >= 0) b = fmax(b, sh_s[m - 1]);   // full short-list: whatever it displaced scored <= its last entry
+  info[1] = b;
 }
 
 static DeviceOnce g_attr_once;
@@ -601,20 +820,71 @@ int gp_predict(const bbo_gp_state& s, const double* Xq, int64_t q, double* mu, d
   return BBO_OK;
 }
 
+// float64 re-score of the gathered short-list rows (r.Xg[par], r.gi[par], r.tf_s) and the final selection.
+static int refine_rescore(const bbo_gp_state& s, const bbo_acq& acq, const ScoreWorkspace& w, const RefineScratch& r,
+                          int par, int m, int k, double* topk_s, int64_t* topk_i, bool keep_running,
+                          int32_t* nan_count, cudaStream_t st) {
+  const int64_t np = w.np;
+  const int rows = int(ceil_div(m, 64) * 64);
+  prof_begin(kProfKstar, st);
+  k_kstar<double><<<unsigned(rows / 64), 256, 0, st>>>(s.h, r.Xg[par], rows, s.X, s.n, np, s.hyp, s.alpha, r.Ks, r.mu,
+                                                      kRefineRows);
+  BBO_LAUNCH_CHECK();
+  prof_end(kProfKstar, st);
+  prof_begin(kProfVnorm, st);
+  k_refine_vnorm<<<dim3(unsigned(np / 32), unsigned(rows / 64)), Cfg64x32::THREADS, Cfg64x32::SMEM_BYTES, st>>>(
+      r.Ks, s.linv, np, r.part);
+  BBO_LAUNCH_CHECK();
+  prof_end(kProfVnorm, st);
+  prof_begin(kProfSelect, st);
+  k_refine_acq<<<1, kRefineRows, 0, st>>>(s.h, acq, s.hyp, r.mu, r.part, int(np / 32), r.gi[par], r.tf_s, m, k,
+                                          keep_running ? 1 : 0, topk_s, topk_i, r.la_s, r.la_i, r.info, nan_count);
+  BBO_LAUNCH_CHECK();
+  k_topk_seg<<<1, 256, 0, st>>>(r.la_s, r.la_i, 0, int64_t(k) + m, k, topk_s, topk_i);
+  BBO_LAUNCH_CHECK();
+  k_refine_info<<<1, 1, 0, st>>>(topk_s, k, r.sh_s, r.sh_i, m, r.bound, r.info);
+  BBO_LAUNCH_CHECK();
+  prof_end(kProfSelect, st);
+  return BBO_OK;
+}
+
+int refine_info(const void* ws, size_t ws_bytes, int64_t n, int64_t d, int64_t q_chunk, double* info_host,
+                cudaStream_t st) {
+  ScoreWorkspace w;
+  int rc = w.bind(const_cast<void*>(ws), ws_bytes, n, d, q_chunk, BBO_PREC_TF32_REFINE, false);
+  if (rc != BBO_OK) return rc;
+  const RefineScratch r = carve_refine(w.refine, w.np, d);
+  BBO_CUDA_CHECK(cudaMemcpyAsync(info_host, r.info, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  BBO_CUDA_CHECK(cudaStreamSynchronize(st));
+  return BBO_OK;
+}
+
 int gp_score_pool(const bbo_gp_state& s, const bbo_acq& acq, int precision, const void* Xq, int xq_is_f32,
                   int64_t q, int64_t index_offset, int k, double* topk_s, int64_t* topk_i, double* mu_out,
                   double* var_out, double* score_out, int32_t* nan_count, void* ws, size_t ws_bytes,
-                  int64_t q_chunk, bool keep_running, cudaStream_t st) {
+                  int64_t q_chunk, bool keep_running, cudaStream_t st, int refine_flags) {
   if (q < 0 || s.n < 1 || s.h.d < 1) return BBO_ERR_BAD_SHAPE;
   if (k < 1 || k > BBO_TOPK_MAX) return BBO_ERR_BAD_ARG;
-  if (precision != BBO_PREC_FP64 && precision != BBO_PREC_TF32) return BBO_ERR_BAD_ARG;
-  if (precision == BBO_PREC_TF32 && s.linv_tf32 == nullptr) return BBO_ERR_BAD_ARG;
+  if (precision != BBO_PREC_FP64 && precision != BBO_PREC_TF32 && precision != BBO_PREC_TF32_REFINE)
+    return BBO_ERR_BAD_ARG;
+  const bool tf32 = precision != BBO_PREC_FP64;
+  const bool refine = precision == BBO_PREC_TF32_REFINE;
+  if (tf32 && s.linv_tf32 == nullptr) return BBO_ERR_BAD_ARG;
+  if (refine && k > BBO_REFINE_KMAX) return BBO_ERR_BAD_ARG;
   int rc = set_smem_attrs();
   if (rc != BBO_OK) return rc;
   ScoreWorkspace w;
   rc = w.bind(ws, ws_bytes, s.n, s.h.d, q_chunk, precision, false);
   if (rc != BBO_OK) return rc;
-  if (!keep_running) {
+  RefineScratch r{};
+  const int m = refine ? refine_shortlist_len(k) : 0, kseg = refine ? refine_kseg(k) : 0;
+  if (refine) {
+    r = carve_refine(w.refine, w.np, s.h.d);
+    if (!(refine_flags & kRefineContinue)) {
+      k_refine_init<<<1, kRefineRows, 0, st>>>(r.sh_s, r.sh_i, r.bound, kRefineRows);
+      BBO_LAUNCH_CHECK();
+    }
+  } else if (!keep_running) {
     k_topk_init<<<1, BBO_TOPK_MAX, 0, st>>>(topk_s, topk_i, k);
     BBO_LAUNCH_CHECK();
   }
@@ -624,10 +894,29 @@ int gp_score_pool(const bbo_gp_state& s, const bbo_acq& acq, int precision, cons
     prof_begin(kProfSelect, sc);
     const int64_t nb = ceil_div(qc, kSeg);
     static const bool unfused = getenv("BBO_SELECT_UNFUSED") != nullptr;
-    if (!unfused && (nb + 1) * k <= kSeg) {
+    if (refine) {
+      // TF32 scores -> per-segment lists of kseg = 2k entries -> running short-list of m entries (by TF32 score)
+      if (nb * kseg + m > w.list_len) return BBO_ERR_WORKSPACE;
+      k_acq_topk<<<unsigned(nb), 256, 0, sc>>>(
+          s.h, acq, 1, s.hyp, mu_chunk, vpart, nsplit, w.qp, qc, index_offset + c0, kseg,
+          mu_out ? mu_out + c0 : nullptr, var_out ? var_out + c0 : nullptr, score_out ? score_out + c0 : nullptr,
+          nan_count, w.la_s + m, w.la_i + m, nullptr);
+      BBO_LAUNCH_CHECK();
+      k_refine_bound<<<1, 256, 0, sc>>>(w.la_s + m, w.la_i + m, int(nb), kseg, r.bound);
+      BBO_LAUNCH_CHECK();
+      if (nb * kseg + m <= kSeg) {
+        k_topk_merge_running<<<1, 256, 0, sc>>>(w.la_s + m, w.la_i + m, int(nb * kseg), m, r.sh_s, r.sh_i);
+        BBO_LAUNCH_CHECK();
+      } else {   // large chunks: the running short-list goes in front of the segment lists, reduced in levels
+        BBO_CUDA_CHECK(cudaMemcpyAsync(w.la_s, r.sh_s, size_t(m) * sizeof(double), cudaMemcpyDeviceToDevice, sc));
+        BBO_CUDA_CHECK(cudaMemcpyAsync(w.la_i, r.sh_i, size_t(m) * sizeof(int64_t), cudaMemcpyDeviceToDevice, sc));
+        int rc2 = topk_levels(w.la_s, w.la_i, nb * kseg + m, w.lb_s, w.lb_i, m, r.sh_s, r.sh_i, sc);
+        if (rc2 != BBO_OK) return rc2;
+      }
+    } else if (!unfused && (nb + 1) * k <= kSeg) {
       // fused acquisition + per-segment top-k, then one merge with the running list (2 launches per chunk)
       k_acq_topk<<<unsigned(nb), 256, 0, sc>>>(
-          s.h, acq, precision == BBO_PREC_TF32, s.hyp, mu_chunk, vpart, nsplit, w.qp, qc, index_offset + c0, k,
+          s.h, acq, tf32, s.hyp, mu_chunk, vpart, nsplit, w.qp, qc, index_offset + c0, k,
           mu_out ? mu_out + c0 : nullptr, var_out ? var_out + c0 : nullptr, score_out ? score_out + c0 : nullptr,
           nan_count, w.la_s, w.la_i, nullptr);
       BBO_LAUNCH_CHECK();
@@ -635,7 +924,7 @@ int gp_score_pool(const bbo_gp_state& s, const bbo_acq& acq, int precision, cons
       BBO_LAUNCH_CHECK();
     } else {
       k_acq<<<unsigned(ceil_div(qc, 256)), 256, 0, sc>>>(
-          s.h, acq, 1, precision == BBO_PREC_TF32, s.hyp, mu_chunk, vpart, nsplit, w.qp, qc, w.score,
+          s.h, acq, 1, tf32, s.hyp, mu_chunk, vpart, nsplit, w.qp, qc, w.score,
           mu_out ? mu_out + c0 : nullptr, var_out ? var_out + c0 : nullptr, score_out ? score_out + c0 : nullptr,
           nan_count);
       BBO_LAUNCH_CHECK();
@@ -650,7 +939,27 @@ int gp_score_pool(const bbo_gp_state& s, const bbo_acq& acq, int precision, cons
     prof_end(kProfSelect, sc);
     return BBO_OK;
   };
-  if (precision == BBO_PREC_TF32) return q == 0 ? BBO_OK : score_tf32_pipeline(s, w, Xq, xq_is_f32, q, consume, st);
+  if (tf32) {
+    if (q > 0) {
+      rc = score_tf32_pipeline(s, w, Xq, xq_is_f32, q, consume, st);
+      if (rc != BBO_OK) return rc;
+    }
+    if (!refine) return BBO_OK;
+    // rows of the short-list -> the row buffer of this call's parity (the other one holds the previous call's)
+    const int par = (refine_flags & kRefineParity) ? 1 : 0;
+    const bool cont = (refine_flags & kRefineContinue) != 0;
+    if (xq_is_f32)
+      k_refine_gather<float><<<1, 256, 0, st>>>(static_cast<const float*>(Xq), index_offset, q, s.h.d, r.sh_s, r.sh_i,
+                                                m, cont ? r.Xg[par ^ 1] : nullptr, cont ? r.gi[par ^ 1] : nullptr,
+                                                r.Xg[par], r.gi[par], r.tf_s);
+    else
+      k_refine_gather<double><<<1, 256, 0, st>>>(static_cast<const double*>(Xq), index_offset, q, s.h.d, r.sh_s,
+                                                 r.sh_i, m, cont ? r.Xg[par ^ 1] : nullptr,
+                                                 cont ? r.gi[par ^ 1] : nullptr, r.Xg[par], r.gi[par], r.tf_s);
+    BBO_LAUNCH_CHECK();
+    if (refine_flags & kRefineDefer) return BBO_OK;
+    return refine_rescore(s, acq, w, r, par, m, k, topk_s, topk_i, keep_running, nan_count, st);
+  }
   const size_t esz = xq_is_f32 ? sizeof(float) : sizeof(double);
   for (int64_t c0 = 0; c0 < q; c0 += w.qp) {
     const int64_t qc = (q - c0 < w.qp) ? q - c0 : w.qp;

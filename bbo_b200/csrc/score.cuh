@@ -19,6 +19,7 @@ struct ScoreWorkspace {
   double *la_s = nullptr, *lb_s = nullptr;   // top-k ping-pong lists
   int64_t *la_i = nullptr, *lb_i = nullptr;
   void* tf32 = nullptr;        // TF32-mode scratch (score_tf32.cu)
+  void* refine = nullptr;      // BBO_PREC_TF32_REFINE scratch (short-list, gathered rows, small FP64 buffers)
 
   static size_t bytes(int64_t n, int64_t d, int64_t q_chunk, int precision, bool want_full);
   int bind(void* ws, size_t ws_bytes, int64_t n, int64_t d, int64_t q_chunk, int precision, bool want_full);
@@ -26,10 +27,18 @@ struct ScoreWorkspace {
 
 int gp_predict(const bbo_gp_state& s, const double* Xq, int64_t q, double* mu, double* var, double* cov_full,
                void* ws, size_t ws_bytes, int64_t q_chunk, cudaStream_t st);
+// refine_flags (BBO_PREC_TF32_REFINE only; 0 for a self-contained call): the host-pool path scores its staging
+// buffers with kRefineDefer (the short-list and its rows stay in the workspace, nothing is re-scored) and
+// kRefineContinue (the short-list of the previous call, kept in the other row buffer, is merged), and re-scores once
+// on its last call.
+constexpr int kRefineContinue = 1, kRefineDefer = 2, kRefineParity = 4;
 int gp_score_pool(const bbo_gp_state& s, const bbo_acq& acq, int precision, const void* Xq, int xq_is_f32,
                   int64_t q, int64_t index_offset, int k, double* topk_s, int64_t* topk_i, double* mu_out,
                   double* var_out, double* score_out, int32_t* nan_count, void* ws, size_t ws_bytes,
-                  int64_t q_chunk, bool keep_running, cudaStream_t st);
+                  int64_t q_chunk, bool keep_running, cudaStream_t st, int refine_flags = 0);
+int refine_shortlist_len(int k);
+int refine_info(const void* ws, size_t ws_bytes, int64_t n, int64_t d, int64_t q_chunk, double* info_host,
+                cudaStream_t st);
 size_t score_batched_workspace_bytes(int64_t n, int64_t d, int64_t B, int64_t q);
 int gp_score_pool_batched(const bbo_gp_hyper& h, int64_t n, int64_t B, const double* X, const double* hyp,
                           const double* linv, const double* alpha, const bbo_acq* acq_dev, const double* Xq,

@@ -17,6 +17,7 @@
 //                 Triangular: row block nb only contracts k < (nb+1)*256.
 // SASS evidence: UTCHMMA / UTMALDG / LDTM / SYNCS (see profiles/).
 #include <cuda.h>
+#include <mutex>
 #include <vector>
 
 #include <cstdio>
@@ -2188,22 +2189,30 @@ static int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t col
 }
 
 // auxiliary stream + events of the K* / panel software pipeline (created once per device)
+constexpr int kSchedSlots = 4;
 struct Tf32Aux {
   cudaStream_t sk = nullptr;   // K* producer
   cudaStream_t ss = nullptr;   // acquisition + selection
   cudaEvent_t entry = nullptr, kdone[2] = {nullptr, nullptr}, pdone[2] = {nullptr, nullptr},
               sdone[2] = {nullptr, nullptr};
-  // work lists of the persistent panel: two cached shapes (a pool has full chunks and one last chunk), 2 x 64 KB of
-  // library-owned device memory per device, rebuilt by k_panel_schedule only when the shape changes
-  int* sched[2] = {nullptr, nullptr};
-  int64_t sched_key[2] = {0, 0};
-  int sched_next = 0;
+  // work lists of the persistent panel: kSchedSlots cached shapes (a pool has full chunks and one last chunk),
+  // 64 KB of library-owned device memory each, rebuilt by k_panel_schedule only when the shape changes.  The
+  // cache is shared by every stream of the device, so each slot carries two events: `built` (recorded behind
+  // k_panel_schedule; a stream that hits the cache waits for it before its panel reads the list) and `used`
+  // (recorded behind the last panel that read the slot; a rebuild waits for it before overwriting the list).
+  int* sched[kSchedSlots] = {};
+  int64_t sched_key[kSchedSlots] = {};
+  cudaEvent_t built[kSchedSlots] = {}, used[kSchedSlots] = {};
+  uint64_t stamp[kSchedSlots] = {};
+  uint64_t clock = 0;
 };
-static Tf32Aux g_aux[16];
+static Tf32Aux g_aux[64];
+static std::mutex g_aux_mutex;
 static int get_aux(Tf32Aux** out) {
   int dev = 0;
   BBO_CUDA_CHECK(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 16) return BBO_ERR_BAD_ARG;
+  if (dev < 0 || dev >= 64) return BBO_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lock(g_aux_mutex);
   Tf32Aux& a = g_aux[dev];
   if (!a.sk) {
     BBO_CUDA_CHECK(cudaStreamCreateWithFlags(&a.sk, cudaStreamNonBlocking));
@@ -2213,6 +2222,10 @@ static int get_aux(Tf32Aux** out) {
       BBO_CUDA_CHECK(cudaEventCreateWithFlags(&a.kdone[i], cudaEventDisableTiming));
       BBO_CUDA_CHECK(cudaEventCreateWithFlags(&a.pdone[i], cudaEventDisableTiming));
       BBO_CUDA_CHECK(cudaEventCreateWithFlags(&a.sdone[i], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < kSchedSlots; ++i) {
+      BBO_CUDA_CHECK(cudaEventCreateWithFlags(&a.built[i], cudaEventDisableTiming));
+      BBO_CUDA_CHECK(cudaEventCreateWithFlags(&a.used[i], cudaEventDisableTiming));
       BBO_CUDA_CHECK(cudaMalloc(&a.sched[i], size_t(kSchedInts) * sizeof(int)));
     }
   }
@@ -2409,14 +2422,13 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
     }
 #undef BBO_KSTAR_MMA
   } else if (s.h.d <= kFastMaxD) {
-    static int attr_d = 0;
+    static DeviceOnce fast_attr_once;
     const size_t ksm = kstar_fast_smem(s.h.d);
-    if (s.h.d > attr_d) {
+    if (fast_attr_once.first()) {
       BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_f32_fast<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           int(kstar_fast_smem(kFastMaxD))));
       BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_f32_fast<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           int(kstar_fast_smem(kFastMaxD))));
-      attr_d = kFastMaxD;
     }
     if (xq_is_f32)
       k_kstar_f32_fast<float><<<unsigned(qc_pad / 128), 256, ksm, st>>>(s.h, static_cast<const float*>(Xq), qc, t.Xs,
@@ -2517,18 +2529,34 @@ static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
       rc = get_aux(&ax);
       if (rc != BBO_OK) return rc;
       const int64_t key = (int64_t(ntp) << 40) | (int64_t(nblk) << 24) | (int64_t(nc) << 12) | int64_t(gs);
-      int slot = ax->sched_key[0] == key ? 0 : (ax->sched_key[1] == key ? 1 : -1);
-      if (slot < 0) {   // (all users of a list are panels on `st`, stream-ordered behind this launch)
-        slot = ax->sched_next;
-        ax->sched_next ^= 1;
-        k_panel_schedule<<<1, 32, 0, st>>>(ntp, nrp, nc, gs, maxj, ax->sched[slot]);
-        BBO_LAUNCH_CHECK();
-        ax->sched_key[slot] = key;
+      int slot = -1;
+      {
+        std::lock_guard<std::mutex> lock(g_aux_mutex);
+        for (int i = 0; i < kSchedSlots; ++i)
+          if (ax->sched_key[i] == key) slot = i;
+        if (slot >= 0) {
+          // built on some stream earlier: this stream's panel must not read the list before that kernel ran
+          BBO_CUDA_CHECK(cudaStreamWaitEvent(st, ax->built[slot], 0));
+        } else {
+          slot = 0;   // least recently used slot
+          for (int i = 1; i < kSchedSlots; ++i)
+            if (ax->stamp[i] < ax->stamp[slot]) slot = i;
+          if (ax->sched_key[slot] != 0) BBO_CUDA_CHECK(cudaStreamWaitEvent(st, ax->used[slot], 0));
+          k_panel_schedule<<<1, 32, 0, st>>>(ntp, nrp, nc, gs, maxj, ax->sched[slot]);
+          BBO_LAUNCH_CHECK();
+          BBO_CUDA_CHECK(cudaEventRecord(ax->built[slot], st));
+          ax->sched_key[slot] = key;
+        }
+        ax->stamp[slot] = ++ax->clock;
       }
       cfg.gridDim = dim3(unsigned(2 * nc), 1);
       const int* sc = ax->sched[slot];
       double* vp32 = t.vp32[buf];
       BBO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_vnorm_tf32_2sm<true>, mapA, mapB, np_i, qp_i, vp32, shrink, sc, maxj));
+      {
+        std::lock_guard<std::mutex> lock(g_aux_mutex);
+        BBO_CUDA_CHECK(cudaEventRecord(ax->used[slot], st));
+      }
       *nsplit_out = -int(nblk);
       *vpart_out = vp32;
     } else if (two_sm)

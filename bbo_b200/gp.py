@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .abstractions import Surrogate
+from .abstractions import Surrogate, adopt_reference_abcs
 from .kernels import ConstantMean, Matern52Kernel, describe_cov, describe_mean
 
 _F64 = torch.float64
@@ -121,12 +121,16 @@ class CudaGP(Surrogate):
     def __init__(self, X: torch.Tensor, Y: torch.Tensor, mean_module: Optional[nn.Module] = None,
                  cov_module: Optional[nn.Module] = None, *, device="cuda", lr: float = 0.01,
                  epochs: int = 100, noise_variance: float = 1e-6, sign: float = 1.0,
-                 q_chunk: Optional[int] = None):
+                 q_chunk: Optional[int] = None, out_dtype: Optional[torch.dtype] = None):
+        """``out_dtype``: dtype of what ``predict`` returns.  None (default) follows the query's dtype, as the
+        reference does; ``torch.float64`` keeps the library's float64 results even for the float32 features the
+        reference's BODesigner sends, so that the acquisition is evaluated in float64 too."""
         _check_2d("X", X)
         _check_2d("Y", Y)
         if Y.shape[0] != X.shape[0] or Y.shape[1] != 1:
             raise ValueError(f"Y must be (n,1) with n={X.shape[0]}, got {tuple(Y.shape)}")
         self._lib = _lib.load()
+        adopt_reference_abcs(type(self), "Surrogate")
         self._device = _lib.require_cuda(device)
         self._mean_module = (mean_module if mean_module is not None else ConstantMean()).to(self._device)
         self._cov_module = (cov_module if cov_module is not None else Matern52Kernel()).to(self._device)
@@ -141,8 +145,12 @@ class CudaGP(Surrogate):
         self._theta = _Theta(self._mean_module, self._cov_module)
         if self._theta.ard and self._theta.n_ls != self.d:
             raise ValueError(f"ARD lengthscale has {self._theta.n_ls} dims, X has {self.d}")
-        self._q_chunk = int(q_chunk) if q_chunk else default_q_chunk(self.n)
+        # chunks are multiples of 128 candidates, at least 128 (the library rounds the same way)
+        self._q_chunk = max(128, (int(q_chunk) + 127) // 128 * 128) if q_chunk else default_q_chunk(self.n)
         self._q_chunk_auto = not q_chunk
+        self._out_dtype = out_dtype
+        self._sm_count = torch.cuda.get_device_properties(self._device).multi_processor_count
+        self._last_refine = None
         self._state = None           # (GpState, keep-alive tensors)
         self._ws = {}                # workspace cache
         self.last_values = None      # objective value seen at each epoch of the last train()
@@ -211,7 +219,12 @@ class CudaGP(Surrogate):
 
     def train(self, X=None, Y=None, *, warm_start: bool = False):
         """GP.train (gp.py:54-63).  The whole epochs x (factorise, gradient, Adam) loop is enqueued on
-        the current stream without host synchronisation; parameters are written back to the modules."""
+        the current stream without host synchronisation; parameters are written back to the modules.
+        ``X`` / ``Y`` exist only because the ``Surrogate`` ABC declares them (abstractions.py:78-81); like the
+        reference's ``GP.train()`` the data given to the constructor is used, so passing them is an error."""
+        if X is not None or Y is not None:
+            raise TypeError("CudaGP.train() uses the data given to the constructor (as GP.train does, gp.py:54); "
+                            "build a new CudaGP or use append() for new observations")
         with torch.cuda.device(self._device):
             th = self._theta
             theta = th.pack(self._device)
@@ -306,6 +319,8 @@ class CudaGP(Surrogate):
             self._Y = y_all[:self.n].contiguous()
             yn = y_all[self.n:].contiguous()
         if xn.shape[0] == 0:
+            if Y_all is not None:
+                self._state = None       # alpha depends on the labels: re-factorise lazily with the new ones
             return
         s = self._ensure_state()
         with torch.cuda.device(self._device):
@@ -381,6 +396,8 @@ class CudaGP(Surrogate):
         if not isinstance(query_X, torch.Tensor):
             raise TypeError(f"Expected Tensor, got {type(query_X)}")
         out_dtype = query_X.dtype if query_X.dtype.is_floating_point else _F64
+        if self._out_dtype is not None:
+            out_dtype = self._out_dtype
         if query_X.dim() == 2:
             mu, cov = self._predict_full(_as_2d_f64(query_X, self._device))
             return mu.reshape(-1, 1).to(out_dtype), cov.to(out_dtype)
@@ -411,8 +428,16 @@ class CudaGP(Surrogate):
             raise ValueError(f"pool must be (q,{self.d}), got {tuple(Xq.shape)}")
         if not (1 <= k <= _lib.TOPK_MAX):
             raise ValueError(f"k must be in [1,{_lib.TOPK_MAX}]")
-        prec = {"fp64": _lib.PREC_FP64, "tf32": _lib.PREC_TF32}[precision]
-        s = self._ensure_state(want_tf32=prec == _lib.PREC_TF32)
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
+        prec = _lib.PRECISIONS[precision]
+        refine = prec == _lib.PREC_TF32_REFINE
+        if refine and k > _lib.REFINE_KMAX:
+            raise ValueError(f"precision='tf32+refine' supports k <= {_lib.REFINE_KMAX}")
+        if host_pool and (running is not None or return_all):
+            raise ValueError("host_pool=True streams the pool from host memory and returns only the selection: "
+                             "`running` and `return_all` are not supported with it")
+        s = self._ensure_state(want_tf32=prec != _lib.PREC_FP64)
         a = as_descriptor(acq)
         is_f32 = Xq.dtype == torch.float32
         if not is_f32 and Xq.dtype != _F64:
@@ -420,9 +445,10 @@ class CudaGP(Surrogate):
         q = Xq.shape[0]
         with torch.cuda.device(self._device):
             qc = min(self._q_chunk, max(128, (q + 127) // 128 * 128))
-            if prec == _lib.PREC_TF32 and q >= 148 * 128 and self._q_chunk_auto:
-                # one 128-candidate tile per SM and per wave: chunks of 148 x 128 candidates
-                qc = min(q // (148 * 128), max(1, (_KS_BUDGET_MB << 20) // (148 * 128 * self.np * 4))) * 148 * 128
+            wave = self._sm_count * 128      # one 128-candidate tile per SM and per wave
+            if prec != _lib.PREC_FP64 and q >= wave and self._q_chunk_auto:
+                qc = min(q // wave, max(1, (_KS_BUDGET_MB << 20) // (wave * self.np * 4))) * wave
+            self._score_shape = (qc, prec)
             ws = self._workspace("score%d" % prec,
                                  int(self._lib.bbo_gp_score_workspace_bytes(self.n, self.d, qc, prec)))
             if running is not None:
@@ -435,8 +461,9 @@ class CudaGP(Surrogate):
                 if Xq.is_cuda:
                     raise ValueError("host_pool=True expects a CPU tensor")
                 xq = Xq.contiguous()
+                qcr = max(128, (qc + 127) // 128 * 128)      # the library's rounding (bbo_b200.h)
                 staging = self._workspace("staging%d" % int(is_f32),
-                                          2 * _lib.HOST_STAGE_CHUNKS * qc * self.d * (4 if is_f32 else 8))
+                                          2 * _lib.HOST_STAGE_CHUNKS * qcr * self.d * (4 if is_f32 else 8))
                 hs = torch.empty(k, dtype=_F64)
                 hi = torch.empty(k, dtype=torch.int64)
                 _lib.check(self._lib.bbo_gp_score_pool_host(
@@ -459,3 +486,23 @@ class CudaGP(Surrogate):
         if return_all:
             return top_s, top_i, mu, var, sc
         return top_s, top_i
+
+    def refine_certificate(self, factor: float = 4.0) -> dict:
+        """Evidence of the last ``precision="tf32+refine"`` call (``bbo_gp_refine_info``; synchronises):
+        ``kth_score`` the k-th best float64 score returned, ``unscored_bound`` an upper bound of the TF32 score of
+        every candidate that was not re-scored, ``tf32_error`` the largest |TF32 - float64| score difference seen on
+        the short-list, ``shortlist`` its size, and ``certified`` = the margin kth_score - unscored_bound exceeds
+        ``factor`` x tf32_error (or nothing was left unscored): no unscored candidate can belong to the float64
+        top-k, i.e. the selection equals the ``precision="fp64"`` selection."""
+        qc, prec = getattr(self, "_score_shape", (None, None))
+        if prec != _lib.PREC_TF32_REFINE:
+            raise RuntimeError("no tf32+refine call has been made")
+        ws = self._ws["score%d" % prec]
+        info = (C.c_double * 4)()
+        with torch.cuda.device(self._device):
+            _lib.check(self._lib.bbo_gp_refine_info(_lib.ptr(ws), ws.numel(), self.n, self.d, qc, info,
+                                                    _lib.stream_ptr(self._device)), "bbo_gp_refine_info")
+        kth, bound, err, cnt = (float(v) for v in info)
+        margin = kth - bound
+        return {"kth_score": kth, "unscored_bound": bound, "tf32_error": err, "shortlist": int(cnt),
+                "margin": margin, "certified": bool(bound == float("-inf") or margin > factor * err)}

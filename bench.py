@@ -7,11 +7,22 @@ step     one pass of the hot path over one candidate pool per GPU:
 value    pool already resident in HBM when the timed region starts
 e2e      same metric through the C-ABI host entry point (bbo_gp_score_pool_host): the pool lives
          in pinned HOST memory; H2D of the pool and D2H of the selection are inside the timed region
-also     "fit": GP fit ms/iter (value + analytic gradient, FP64) next to the CPU oracle's s/iter;
-         "roofline" for the dominant kernel; "cpu_baseline" (oracle port on the host cores)
+also     "fit": GP fit ms/iter (value + analytic gradient, FP64) next to cuSOLVER and the CPU s/iter;
+         "roofline" for the dominant kernel; "cpu_baseline" (the UNMODIFIED reference on the host cores)
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp64|tf32] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--precision tf32+refine|tf32|fp64] [--impl reference]
+                  [--scaling weak|strong --pool-total Q] [--n N --d D --objective ackley|levy|rastrigin]
 For N > 1 launch with torchrun (one rank per GPU); rank 0 prints ONE JSON line.
+
+precision  "tf32+refine" (default): tcgen05 TF32 panel over the whole pool keeps a short-list, the short-list is
+           re-scored in float64, the selection and the returned scores are float64 (identical to --precision fp64:
+           checked in the run, `selection_matches_fp64`).  "tf32": TF32-accurate scores.  "fp64": DMMA throughout.
+scaling    "weak" (default): --pool candidates per GPU.  "strong": --pool-total candidates split over the GPUs
+           (BASELINE config 5: --scaling strong --pool-total 67108864 --n 8192 --d 100 --objective levy).
+reference  --impl reference runs the UNMODIFIED reference (vendored to baseline/_ref by
+           baseline/vendor_reference.py): GP.predict in chunks -> .diagonal() -> EI -> top-k
+           (bbo/algorithms/surrogates/gp/gp.py:65-83, designers/bo/acquisitions.py:18-23) on all host cores, on a
+           bounded sample of the same pool; the oracle port is timed beside it (`cpu_port`).
 """
 import argparse
 import json
@@ -38,66 +49,147 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="tf32", choices=["fp64", "tf32"],
-                    help="arithmetic of the n^2 panel in the headline number (the other mode is reported too)")
+    ap.add_argument("--precision", default="tf32+refine", choices=["fp64", "tf32", "tf32+refine"],
+                    help="arithmetic of the n^2 panel in the headline number (fp64 is reported beside it)")
     ap.add_argument("--no-other-mode", action="store_true")
     ap.add_argument("--n", type=int, default=N_OBS)
     ap.add_argument("--d", type=int, default=DIM)
-    ap.add_argument("--pool", type=int, default=1 << 20, help="candidates per GPU per step")
+    ap.add_argument("--objective", default="ackley", choices=["ackley", "levy", "rastrigin"])
+    ap.add_argument("--lengthscale", type=float, default=None, help="default 0.5 (1.5 for d >= 50)")
+    ap.add_argument("--pool", type=int, default=1 << 20, help="candidates per GPU per step (weak scaling)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--pool-total", type=int, default=1 << 26, help="candidates per step, all GPUs (strong scaling)")
     ap.add_argument("--cpu-sample", type=int, default=4096, help="candidates per CPU-baseline step")
     ap.add_argument("--no-fit", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-verify", action="store_true", help="skip the single-GPU re-score of the global pool")
+    a = ap.parse_args()
+    if a.lengthscale is None:
+        a.lengthscale = LENGTHSCALE if a.d < 50 else 1.5
+    return a
 
 
-def workload_name(a):
-    return (f"GP-BO EI pool scoring: Ackley-{a.d}D, n={a.n} observations, ARD RBF (l=0.5, s2=1, "
-            f"noise=1e-4), {a.pool} uniform candidates per GPU per step, top-{TOPK}")
+def world_size(a):
+    return int(os.environ.get("WORLD_SIZE", str(max(1, a.gpus)))) if a.impl == "b200" else max(1, a.gpus)
+
+
+def pool_per_gpu(a, world):
+    return a.pool if a.scaling == "weak" else -(-a.pool_total // world)
+
+
+def config_dict(a, world):
+    """The same dict from both arms (the driver compares them)."""
+    per = pool_per_gpu(a, world)
+    total = per * world if a.scaling == "weak" else a.pool_total
+    return {"workload": (f"GP-BO EI pool scoring: {a.objective.capitalize()}-{a.d}D, n={a.n} observations, ARD RBF "
+                         f"(l={a.lengthscale:g}, s2=1, noise=1e-4), uniform candidate pool, top-{TOPK}"),
+            "n": a.n, "d": a.d, "k": TOPK, "pool_per_gpu": per, "pool_total": total, "scaling": a.scaling,
+            "parallelism": f"pool sharded x{world}, 1 all-gather of top-k",
+            "l2": "inputs larger than L2 (pool + L^-1 per pass)"}
 
 
 def problem(a):
-    from bbo_b200.benchmarks import Ackley, make_observations
-    X, y = make_observations(Ackley(a.d), a.n, SEED)
-    raw_ls = float(np.log(np.expm1(LENGTHSCALE)))      # softplus^-1(0.5)
+    from bbo_b200.benchmarks import Ackley, Levy, Rastrigin, make_observations
+    func = {"ackley": Ackley, "levy": Levy, "rastrigin": Rastrigin}[a.objective](a.d)
+    X, y = make_observations(func, a.n, SEED)
+    raw_ls = float(np.log(np.expm1(a.lengthscale)))      # softplus^-1
     raw_var = float(np.log(np.expm1(1.0)))
     return X, y, raw_ls, raw_var
 
 
 # ------------------------------------------------------------------------------------------
-# reference arm / CPU baseline: the oracle port (the reference is pure Python and cannot travel
-# to the GPU box; oracle/gp_oracle.py restates its arithmetic and is pinned to it by goldens)
+# CPU arms: the unmodified reference (baseline/_ref) and the oracle port
 # ------------------------------------------------------------------------------------------
 def cpu_pool_sample(a, count):
     rng = np.random.default_rng(SEED + 1)
     return rng.random((count, a.d))
 
 
-def cpu_state(a):
-    from oracle import gp_oracle as O
-    X, y, raw_ls, raw_var = problem(a)
-    p = O.GPParams(kind=O.RBF, raw_lengthscale=np.full(a.d, raw_ls), raw_variance=raw_var, constant=0.0,
-                   noise=NOISE)
-    state = O.solve_gp_linear_system(p, X, y)
-    return O, p, X, y, state
+def reference_available():
+    from baseline.ref_env import reference_path
+    return reference_path() is not None
 
 
-def cpu_score_rate(a, steps, warmup):
-    """cand/s of the CPU oracle on `cpu_sample` candidates per step, best chunk of {256, 1024}."""
-    O, p, X, y, state = cpu_state(a)
-    Xq = cpu_pool_sample(a, a.cpu_sample)
-    best_f = float(y.max())
+class ReferenceArm:
+    """The reference's own classes on this host's cores, float64, fixed hyper-parameters."""
+
+    def __init__(self, a):
+        from baseline.ref_env import setup_reference
+        self.path = setup_reference()
+        from bbo.algorithms.designers.bo.acquisitions import EI
+        from bbo.algorithms.surrogates.gp import GP
+        from bbo.algorithms.surrogates.gp.kernels import RBFKernel, ScaleKernel
+        from bbo.algorithms.surrogates.gp.means import ConstantMean
+        from bbo.algorithms.surrogates.gp.objectives import neg_log_marginal_likelihood
+        X, y, raw_ls, raw_var = problem(a)
+        self.a = a
+        self.X = torch.as_tensor(X)
+        self.Y = torch.as_tensor(y).reshape(-1, 1)
+        self.cov = ScaleKernel(RBFKernel(ard_dim=a.d)).double()
+        self.mean = ConstantMean().double()
+        with torch.no_grad():
+            self.cov.base_kernel.lengthscale.fill_(raw_ls)
+            self.cov.variance.fill_(raw_var)
+        self.gp = GP(self.X, self.Y, self.mean, self.cov, noise_variance=NOISE, epochs=0)
+        self.ei = EI(float(y.max()))
+        self.nll = neg_log_marginal_likelihood
+
+    def score(self, Xq: torch.Tensor, chunk: int):
+        """GP.predict (gp.py:65-83) in 2-D chunks -> .diagonal() -> EI (acquisitions.py:18-23) -> top-k."""
+        out = []
+        with torch.no_grad():
+            for c0 in range(0, Xq.shape[0], chunk):
+                mu, cov = self.gp.predict(Xq[c0:c0 + chunk])
+                out.append(self.ei(mu.reshape(-1), cov.diagonal().sqrt()))
+        sc = torch.cat(out)
+        return torch.topk(sc, min(TOPK, sc.numel()))
+
+    def fit_iter(self):
+        """objectives.py:34-45 + backward (gp.py:58-62): one fit iteration."""
+        for p in list(self.mean.parameters()) + list(self.cov.parameters()):
+            p.grad = None
+        loss = self.nll(self.X, self.Y, self.mean, self.cov, NOISE)
+        loss.backward()
+        return float(loss)
+
+
+class PortArm:
+    def __init__(self, a):
+        from oracle import gp_oracle as O
+        X, y, raw_ls, raw_var = problem(a)
+        self.O, self.X, self.y = O, X, y
+        self.p = O.GPParams(kind=O.RBF, raw_lengthscale=np.full(a.d, raw_ls), raw_variance=raw_var, constant=0.0,
+                            noise=NOISE)
+        self.state = O.solve_gp_linear_system(self.p, X, y)
+        self.best_f = float(y.max())
+
+    def score(self, Xq, chunk):
+        return self.O.score_pool(self.p, self.X, self.y, Xq, "ei", self.best_f, k=TOPK, state=self.state, chunk=chunk)
+
+    def fit_iter(self):
+        return self.O.objective_value_and_grad(self.p, self.X, self.y)
+
+
+def cpu_rate(arm, Xq, steps, warmup, chunks=(64, 256, 1024)):
+    """(cand/s, s/step, chunk): quick sweep of the chunk size on a slice, then `warmup` + `steps` timed passes."""
+    probe = Xq[:min(len(Xq), 1024)]
     best = None
-    for chunk in (256, 1024):
-        for _ in range(max(1, min(warmup, 1))):
-            O.score_pool(p, X, y, Xq[:chunk], "ei", best_f, k=TOPK, state=state, chunk=chunk)
+    arm.score(probe[:64], 64)            # the first predict caches the factorisation (gp.py:66-74)
+    for chunk in chunks:
         t0 = time.perf_counter()
-        for _ in range(steps):
-            O.score_pool(p, X, y, Xq, "ei", best_f, k=TOPK, state=state, chunk=chunk)
-        dt = (time.perf_counter() - t0) / steps
+        arm.score(probe, chunk)
+        dt = time.perf_counter() - t0
         if best is None or dt < best[0]:
             best = (dt, chunk)
-    return a.cpu_sample / best[0], best[0], best[1]
+    chunk = best[1]
+    for _ in range(warmup):
+        arm.score(Xq, chunk)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        arm.score(Xq, chunk)
+    dt = (time.perf_counter() - t0) / steps
+    return len(Xq) / dt, dt, chunk
 
 
 def emit_line(line):   # rebound by main() to the saved stdout descriptor
@@ -109,16 +201,23 @@ def run_reference(a):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    steps = max(1, min(a.steps, 5))
-    rate, dt, chunk = cpu_score_rate(a, steps, a.warmup)
+    world = world_size(a)
+    use_ref = reference_available()
+    arm = ReferenceArm(a) if use_ref else PortArm(a)
+    Xq_np = cpu_pool_sample(a, a.cpu_sample)
+    Xq = torch.as_tensor(Xq_np) if use_ref else Xq_np
+    rate, dt, chunk = cpu_rate(arm, Xq, a.steps, min(a.warmup, 1))
     cores = torch.get_num_threads()
-    sample = f"{a.cpu_sample} candidates/step, chunk {chunk}, oracle port (torch CPU float64)"
+    kind = "reference" if use_ref else "port"
+    what = ("unmodified reference (baseline/_ref): GP.predict 2-D chunks -> diagonal -> EI -> topk, torch CPU float64"
+            if use_ref else "oracle port (torch CPU float64); baseline/_ref absent")
+    sample = f"{a.cpu_sample} candidates/step of the same pool, chunk {chunk}, {what}"
     line = {
         "impl": "reference", "metric": "EI candidates scored/sec", "value": rate, "unit": "candidates/s",
-        "n_gpus": a.gpus, "steps": steps, "warmup": a.warmup, "ms_per_step": dt * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(a), "n": a.n, "d": a.d},
-        "cpu_baseline": {"value": rate, "unit": "candidates/s", "cores": cores, "kind": "port", "sample": sample},
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(a, world),
+        "cpu_baseline": {"value": rate, "unit": "candidates/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -176,17 +275,22 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def measured_peaks():
-    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+def load_json(path):
     try:
         return json.load(open(path))
     except Exception:  # noqa: BLE001
         return None
 
 
+def stored_peaks():
+    """profiles/measured_peaks_tf32_f64.json: cuBLAS TF32 / FP64 GEMM peaks measured ONCE on this pool's B200 with the
+    method of MEASURED_PEAKS.json (tools/measure_peaks.py) -- the driver's file has bf16 only.  A stored denominator
+    keeps roofline.frac comparable from run to run (a live one moved 708 -> 758 TFLOP/s across round 1's runs)."""
+    return load_json(os.path.join(ROOT, "profiles", "measured_peaks_tf32_f64.json"))
+
+
 def live_matmul_peak(dtype, tf32, n=4096, reps=10):
-    """cuBLAS GEMM throughput measured the way MEASURED_PEAKS.json measured bf16 (best of 10,
-    CUDA events) -- the driver file has no FP64/TF32 entry, so the denominator is measured here."""
+    """cuBLAS GEMM throughput, best of `reps`, CUDA events (fallback when the stored peaks are absent)."""
     old = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = tf32
     a = torch.randn(n, n, dtype=dtype, device="cuda")
@@ -207,39 +311,44 @@ def live_matmul_peak(dtype, tf32, n=4096, reps=10):
     return 2.0 * n ** 3 / best / 1e9   # TFLOP/s
 
 
-def live_matmul_sustained(dtype, tf32, n=4096, seconds=2.0):
-    """The same GEMM back to back for `seconds` (MEASURED_PEAKS.json's "sustained" method, there 4 s for bf16): the
-    denominator for a kernel that is timed inside a long step, where the chip sits at its power cap."""
-    old = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = tf32
-    a = torch.randn(n, n, dtype=dtype, device="cuda")
-    b = torch.randn(n, n, dtype=dtype, device="cuda")
+def peaks_for(tag):
+    """(burst, sustained, source) TFLOP/s for the panel dtype: stored file first, live measurement otherwise."""
+    sp = stored_peaks()
+    key = "f64" if tag == "vnorm" else "tf32"
+    if sp and f"{key}_tflops" in sp:
+        return sp[f"{key}_tflops"], sp.get(f"{key}_tflops_sustained"), \
+            f"profiles/measured_peaks_tf32_f64.json ({sp.get('how', 'cuBLAS GEMM, MEASURED_PEAKS.json method')})"
+    if key == "f64":
+        return live_matmul_peak(torch.float64, False), None, "measured live: cuBLAS f64 GEMM 4096^3 best of 10"
+    return live_matmul_peak(torch.float32, True, n=8192), None, "measured live: cuBLAS tf32 GEMM 8192^3 best of 10"
+
+
+def cusolver_fit_ms(n, reps=3):
+    """Library bar for the fit's dense part: cuSOLVER potrf + potri through torch.linalg on an SPD n x n float64
+    matrix (the Cholesky and the K^-1 the gradient needs; the fit also builds K and reduces the gradient)."""
+    g = torch.Generator(device="cuda").manual_seed(1)
+    A = torch.randn(n, n, dtype=torch.float64, device="cuda", generator=g)
+    K = A @ A.T / n + torch.eye(n, dtype=torch.float64, device="cuda")
+    del A
     for _ in range(2):
-        a @ b
+        L = torch.linalg.cholesky(K)
+        torch.cholesky_inverse(L)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record()
-    a @ b
-    e1.record()
-    torch.cuda.synchronize()
-    reps = max(8, int(seconds * 1e3 / max(e0.elapsed_time(e1), 1e-3)))
     e0.record()
     for _ in range(reps):
-        a @ b
+        L = torch.linalg.cholesky(K)
+        torch.cholesky_inverse(L)
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    torch.backends.cuda.matmul.allow_tf32 = old
-    del a, b
-    return 2.0 * n ** 3 * reps / ms / 1e9, reps, time.perf_counter() - t0
+    return e0.elapsed_time(e1) / reps
 
 
 def run_b200(a):
     import torch.distributed as dist
     import bbo_b200 as B
     from bbo_b200 import _lib
-    from bbo_b200.distributed import broadcast_state, sharded_score_pool
+    from bbo_b200.distributed import broadcast_state, gather_topk, merge_topk_device, shard_range
     from bbo_b200.pool import uniform_pool
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -257,6 +366,13 @@ def run_b200(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
     X, y, raw_ls, raw_var = problem(a)
     cov = B.ScaleKernel(B.RBFKernel(ard_dim=a.d)).double()
     with torch.no_grad():
@@ -264,21 +380,57 @@ def run_b200(a):
         cov.variance.fill_(raw_var)
     gp = B.CudaGP(torch.as_tensor(X), torch.as_tensor(y).reshape(-1, 1), B.ConstantMean().double(), cov,
                   device=dev, noise_variance=NOISE, epochs=1)
+    bc0, bc1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    bc0.record()
     if world > 1:
-        broadcast_state(gp, src=0)       # fit/factorise on rank 0 only, replicate L^-1 and alpha
-    else:
-        gp.state
+        broadcast_state(gp, src=0)       # hyper-parameters from the fitting rank; every rank factorises once
+    gp.state
+    bc1.record()
+    barrier()
+    state_ms = max_over_ranks(bc0.elapsed_time(bc1))
     acq = B.EI(float(y.max()))
-    q = a.pool
-    lo = rank * q                                              # weak scaling: q candidates per GPU
-    Xq = uniform_pool(SEED + 1, lo, q, a.d, device=dev)        # float64 (q,d): 168 MB at 2^20 x 20 > L2
+    if a.scaling == "weak":
+        q = a.pool
+        lo = rank * q
+        q_total = world * q
+    else:
+        q_total = a.pool_total
+        lo, hi = shard_range(q_total, rank, world)
+        q = hi - lo
+    # device-resident pool (float64); when the shard does not fit comfortably it is generated in slabs per step
+    slab = min(q, max(1 << 20, (2 << 30) // (8 * a.d)))
+    resident = q <= slab
+    Xq = uniform_pool(SEED + 1, lo, min(q, slab), a.d, device=dev)
     lib = _lib.load()
+    coll_ev = []
 
-    def step():
-        return sharded_score_pool(gp, acq, TOPK, Xq, lo, precision=a.precision)
+    def score_shard(precision):
+        """This rank's shard -> (scores[k], indices[k]) on the device (slabs merged through `running`)."""
+        if resident:
+            return gp.score_pool(Xq, acq, TOPK, precision=precision, index_offset=lo)
+        run = None
+        for s0 in range(0, q, slab):
+            qs = min(slab, q - s0)
+            uniform_pool(SEED + 1, lo + s0, qs, a.d, device=dev, out=Xq[:qs])
+            run = gp.score_pool(Xq[:qs], acq, TOPK, precision=precision, index_offset=lo + s0, running=run)
+        return run
+
+    def step(precision=a.precision, timed=True):
+        s, i = score_shard(precision)
+        if world == 1:
+            return s, i
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        gs, gi = gather_topk(s, i)                       # ONE all_gather_into_tensor of k (score, index) pairs
+        out = merge_topk_device(gs, gi, TOPK)
+        c1.record()
+        if timed:
+            coll_ev.append((c0, c1))
+        return out
 
     for _ in range(a.warmup):
-        step()
+        step(timed=False)
     barrier()
     clocks = ClockSampler(local)
     if rank == 0:
@@ -291,26 +443,29 @@ def run_b200(a):
         top_s, top_i = step()
     e1.record()
     barrier()
-    ms = e0.elapsed_time(e1)
+    ms = max_over_ranks(e0.elapsed_time(e1))
     launches = lib.bbo_launch_count() - l0
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     clk = clocks.stop() if rank == 0 else None
-    value = world * q * a.steps / (ms * 1e-3)
+    value = q_total * a.steps / (ms * 1e-3)
+    collective_ms = None
+    if world > 1:
+        collective_ms = max_over_ranks(sum(c0.elapsed_time(c1) for c0, c1 in coll_ev) / max(len(coll_ev), 1))
+    cert = gp.refine_certificate() if a.precision == "tf32+refine" else None
 
-    # ---- e2e: pool in pinned host memory, through bbo_gp_score_pool_host
+    # ---- e2e: pool in pinned host memory (float32, the dtype of the reference's features), through
+    #      bbo_gp_score_pool_host: H2D of every candidate and D2H of the selection inside the timed region
     e2e = None
     if not a.no_e2e:
-        Xh = torch.empty(q, a.d, dtype=torch.float64).pin_memory()
-        Xh.copy_(Xq)
+        qh = min(q, slab)
+        Xh = torch.empty(qh, a.d, dtype=torch.float32).pin_memory()
+        if not resident:
+            uniform_pool(SEED + 1, lo, qh, a.d, device=dev, out=Xq[:qh])
+        Xh.copy_(Xq[:qh])
         torch.cuda.synchronize()
 
         def step_host():
             hs, hi = gp.score_pool(Xh, acq, TOPK, precision=a.precision, index_offset=lo, host_pool=True)
             if world > 1:   # same single all-gather + merge on the gathered lists
-                from bbo_b200.distributed import gather_topk, merge_topk_device
                 gs, gi = gather_topk(hs.to(dev), hi.to(dev))
                 ms_, mi_ = merge_topk_device(gs, gi, TOPK)
                 return ms_.cpu(), mi_.cpu()
@@ -324,94 +479,100 @@ def run_b200(a):
             hs, hi = step_host()
         e1.record()
         barrier()
-        ms_h = e0.elapsed_time(e1)
+        ms_h = max_over_ranks(e0.elapsed_time(e1))
+        # the device run scored the same candidates in float64; compare selections on the float32 pool
+        ds, di = gp.score_pool(Xh.to(dev), acq, TOPK, precision="fp64", index_offset=lo)
         if world > 1:
-            t = torch.tensor([ms_h], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_h = float(t.item())
-        e2e = {"value": world * q * a.steps / (ms_h * 1e-3), "unit": "candidates/s",
-               "h2d_bytes_per_step": q * a.d * 8, "d2h_bytes_per_step": TOPK * 16,
-               "ms_per_step": ms_h / a.steps,
-               "selection_matches_device_run": bool(torch.equal(hi.cpu(), top_i.cpu()))}
+            gs, gi = gather_topk(ds, di)
+            ds, di = merge_topk_device(gs, gi, TOPK)
+        e2e = {"value": world * qh * a.steps / (ms_h * 1e-3), "unit": "candidates/s",
+               "h2d_bytes_per_step": qh * a.d * 4, "d2h_bytes_per_step": TOPK * 16,
+               "ms_per_step": ms_h / a.steps, "host_pool_dtype": "float32", "candidates_per_gpu_per_step": qh,
+               "selection_matches_fp64": bool(torch.equal(hi.cpu(), di.cpu()))}
         del Xh
 
-    # ---- the other precision mode, same workload, fewer steps (reported beside the headline)
+    # ---- float64 mode on the same candidates: the parity anchor of the headline mode, and its throughput.  When the
+    #      shard is generated in slabs (strong scaling at config-5 sizes) the comparison runs on its first slab.
     other = None
-    if not a.no_other_mode:
-        oprec = "fp64" if a.precision == "tf32" else "tf32"
-        osteps = 2 if oprec == "fp64" else a.steps
-        sharded_score_pool(gp, acq, TOPK, Xq, lo, precision=oprec)
+    sel_match = None
+    if not a.no_other_mode and a.precision != "fp64":
+        qs = min(q, slab)
+        if not resident:
+            uniform_pool(SEED + 1, lo, qs, a.d, device=dev, out=Xq[:qs])
+
+        def sub_step(precision):
+            s_, i_ = gp.score_pool(Xq[:qs], acq, TOPK, precision=precision, index_offset=lo)
+            if world > 1:
+                gs, gi = gather_topk(s_, i_)
+                return merge_topk_device(gs, gi, TOPK)
+            return s_, i_
+
+        hs_, hi_ = sub_step(a.precision)
+        osteps = 2
+        sub_step("fp64")
         barrier()
         e0.record()
         for _ in range(osteps):
-            os_, oi_ = sharded_score_pool(gp, acq, TOPK, Xq, lo, precision=oprec)
+            os_, oi_ = sub_step("fp64")
         e1.record()
         barrier()
-        oms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([oms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            oms = float(t.item())
-        other = {"precision": oprec, "value": world * q * osteps / (oms * 1e-3), "unit": "candidates/s",
-                 "ms_per_step": oms / osteps, "steps": osteps,
-                 "top1_index_matches_headline_mode": bool(int(oi_[0]) == int(top_i[0]))}
+        oms = max_over_ranks(e0.elapsed_time(e1))
+        sel_match = bool(torch.equal(oi_, hi_))
+        other = {"precision": "fp64", "value": world * qs * osteps / (oms * 1e-3), "unit": "candidates/s",
+                 "ms_per_step": oms / osteps, "steps": osteps, "candidates_per_gpu_per_step": qs,
+                 "max_rel_score_diff_vs_headline": float(((os_ - hs_).abs() / os_.abs().clamp_min(1e-300)).max())}
 
-    # ---- roofline of the dominant kernel: separate profiled pass (CUDA events on the launch stream)
-    roof = None
-    fit = None
-    cpu = None
+    # ---- N > 1: the sharded selection against ONE GPU scoring the whole pool alone (after the timed region)
+    single = None
+    if world > 1 and not a.no_verify and rank == 0:
+        run = None
+        for s0 in range(0, q_total, slab):
+            qs = min(slab, q_total - s0)
+            buf = uniform_pool(SEED + 1, s0, qs, a.d, device=dev)
+            run = gp.score_pool(buf, acq, TOPK, precision=a.precision, index_offset=s0, running=run)
+            del buf
+        single = bool(torch.equal(run[1], top_i) and torch.equal(run[0], top_s))
+
+    roof = fit = cpu = cpu_port = None
     if rank == 0:
+        # ---- roofline of the dominant kernel: separate profiled pass (CUDA events on the launch stream)
         tag = "vnorm" if a.precision == "fp64" else "tf32"
+        npasses = max(1, min(a.steps, 3))
+        qprof = min(q, slab)
         lib.bbo_profile_enable(1)
-        for _ in range(max(1, min(a.steps, 3))):
-            gp.score_pool(Xq, acq, TOPK, precision=a.precision, index_offset=lo)
+        for _ in range(npasses):
+            gp.score_pool(Xq[:qprof], acq, TOPK, precision=a.precision, index_offset=lo)
         regions, tot_ms = _lib.profile_read(tag)
         kregions, ktot = _lib.profile_read("kstar")
         sregions, stot = _lib.profile_read("select")
+        if tag == "tf32":
+            vregions, vtot = _lib.profile_read("vnorm")       # the float64 re-score of the short-list
+        else:
+            vregions, vtot = 0, 0.0
         lib.bbo_profile_enable(0)
-        npasses = max(1, min(a.steps, 3))
-        flops_per_launch = float(a.n) * a.n * (q * npasses / max(regions, 1))   # n^2 per candidate
+        flops_per_launch = float(a.n) * a.n * (qprof * npasses / max(regions, 1))   # n^2 per candidate
         avg_ms = tot_ms / max(regions, 1)
         achieved = flops_per_launch / (avg_ms * 1e-3) / 1e12
-        if a.precision == "fp64":
-            peak = live_matmul_peak(torch.float64, False)
-            peak_src = "measured live: cuBLAS f64 GEMM 4096^3 best of 10 (MEASURED_PEAKS.json has no f64 entry)"
-        else:
-            peak = live_matmul_peak(torch.float32, True, n=8192)
-            peak_src = "measured live: cuBLAS tf32 GEMM 8192^3 best of 10 (MEASURED_PEAKS.json has no tf32 entry)"
-        # `peak` stays the burst figure (best of 10: the conservative denominator).  The panel is timed inside a long
-        # step (dozens of back-to-back launches at the power cap), where the matching figure is the SUSTAINED GEMM
-        # rate: reported beside it as peak_sustained / frac_of_sustained.
-        if a.precision == "fp64":
-            peak_sus, sus_reps, _ = live_matmul_sustained(torch.float64, False, n=4096, seconds=1.5)
-        else:
-            peak_sus, sus_reps, _ = live_matmul_sustained(torch.float32, True, n=8192, seconds=1.5)
-        peak_src += (f"; peak_sustained = the same GEMM back to back for {sus_reps} launches (~1.5 s), the method of "
-                     "MEASURED_PEAKS.json's bf16_tflops_sustained")
+        peak, peak_sus, peak_src = peaks_for(tag)
         traffic = None
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        tr = load_json(os.path.join(ROOT, "profiles", "roofline_traffic.json"))
+        if tr:
             traffic = tr.get(tag, {}).get("dram_bytes_per_launch")
-        except Exception:  # noqa: BLE001
-            pass
-        if other is not None:   # panel roofline of the other mode as well (same method)
-            otag = "vnorm" if other["precision"] == "fp64" else "tf32"
-            lib.bbo_profile_enable(1)
-            gp.score_pool(Xq, acq, TOPK, precision=other["precision"], index_offset=lo)
-            oreg, otot = _lib.profile_read(otag)
-            lib.bbo_profile_enable(0)
-            opeak = live_matmul_peak(torch.float64, False) if otag == "vnorm" else live_matmul_peak(torch.float32, True, n=8192)
-            oach = float(a.n) * a.n * q / (otot * 1e-3) / 1e12
-            other["roofline"] = {"bound": "tensor", "kernel": "k_vnorm (DMMA.8x8x4)" if otag == "vnorm" else "k_vnorm_tf32_2sm (tcgen05)",
-                                 "achieved": oach, "peak": opeak, "unit": "TFLOP/s", "frac": oach / opeak,
-                                 "launches_timed": oreg}
-        share = tot_ms / max(tot_ms + ktot + stot, 1e-9)
-        roof = {"bound": "tensor", "kernel": "k_vnorm (DMMA.8x8x4)" if tag == "vnorm" else "k_vnorm_tf32_2sm (tcgen05.mma cta_group::2 kind::tf32)",
+        mp = load_json(os.path.join(ROOT, "MEASURED_PEAKS.json")) or {}
+        share = tot_ms / max(tot_ms + ktot + stot + vtot, 1e-9)
+        roof = {"bound": "tensor",
+                "kernel": "k_vnorm (DMMA.8x8x4)" if tag == "vnorm" else "k_vnorm_tf32_2sm (tcgen05.mma cta_group::2 kind::tf32)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_sustained": peak_sus, "frac_of_sustained": achieved / peak_sus,
+                "peak_sustained": peak_sus, "frac_of_sustained": (achieved / peak_sus) if peak_sus else None,
+                "frac_vs_bf16_half": (achieved / (mp["bf16_tflops"] / 2)) if (tag == "tf32" and "bf16_tflops" in mp) else None,
+                "frac_vs_bf16_half_sustained": (achieved / (mp["bf16_tflops_sustained"] / 2))
+                if (tag == "tf32" and "bf16_tflops_sustained" in mp) else None,
                 "peak_source": peak_src, "launches_timed": regions, "avg_launch_ms": avg_ms,
                 "algorithmic_flops_per_launch": flops_per_launch, "share_of_step": share,
-                "other_kernels_ms": {"kstar": ktot / max(kregions, 1), "select": stot / max(sregions, 1)}}
+                "other_kernels_ms_per_pass": {"kstar": ktot / npasses, "select": stot / npasses,
+                                              "refine_fp64_panel": vtot / npasses}}
+        step_flops = (float(a.n) * a.n + 3.0 * a.n * a.d + 4.0 * a.n) * q_total / world
+        roof["whole_step_tflops_per_gpu"] = step_flops / (ms / a.steps * 1e-3) / 1e12
 
         # ---- GP fit s/iter (metric part ii): value + analytic gradient, FP64
         if not a.no_fit:
@@ -427,15 +588,17 @@ def run_b200(a):
             torch.cuda.synchronize()
             fit_ms = f0.elapsed_time(f1) / nit
             fit_flops = float(a.n) ** 3 + 3.0 * a.n * a.n * a.d
+            peak64, _, src64 = peaks_for("vnorm")
             fit = {"ms_per_iter": fit_ms, "n": a.n, "d": a.d, "dtype": "f64",
                    "achieved_tflops": fit_flops / (fit_ms * 1e-3) / 1e12,
-                   "algorithmic_flops_per_iter": fit_flops}
-            if a.precision != "fp64":
-                peak64 = live_matmul_peak(torch.float64, False)
-            else:
-                peak64 = peak
-            fit["peak_tflops"] = peak64
+                   "algorithmic_flops_per_iter": fit_flops, "peak_tflops": peak64, "peak_source": src64}
             fit["frac"] = fit["achieved_tflops"] / peak64
+            try:
+                fit["cusolver_potrf_potri_ms"] = cusolver_fit_ms(a.n)
+                fit["vs_cusolver"] = fit["cusolver_potrf_potri_ms"] / fit_ms
+            except Exception as e:  # noqa: BLE001
+                fit["cusolver_potrf_potri_ms"] = None
+                fit["cusolver_error"] = str(e)[:200]
             # the same iteration inside GP.train (gp.py:54-63): value + gradient + Adam update per epoch, the epoch
             # replayed as a CUDA graph (what a suggest() pays 100 times); second train() call timed, 20 epochs
             cov_t = B.ScaleKernel(B.RBFKernel(ard_dim=a.d)).double()
@@ -453,33 +616,51 @@ def run_b200(a):
             fit["train_ms_per_epoch"] = f0.elapsed_time(f1) / 20
             del gpt
 
-        # ---- CPU baseline on this host's cores (bounded sample; N=1 only)
+        # ---- CPU baseline on this host's cores (bounded sample; N=1 only): the unmodified reference, port beside it
         if world == 1 and not a.no_cpu:
             torch.set_num_threads(os.cpu_count() or 1)
-            rate, dt, chunk = cpu_score_rate(a, 2, 1)
-            cpu = {"value": rate, "unit": "candidates/s", "cores": torch.get_num_threads(), "kind": "port",
-                   "sample": f"{a.cpu_sample} candidates x 2 steps, chunk {chunk}, oracle port (torch CPU float64)"}
-            if fit is not None:
-                O, p, Xc, yc, _ = cpu_state(a)
+            Xs = cpu_pool_sample(a, a.cpu_sample)
+            port = PortArm(a)
+            prate, pdt, pchunk = cpu_rate(port, Xs, 2, 1, chunks=(256, 1024))
+            cpu_port = {"value": prate, "unit": "candidates/s", "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": f"{a.cpu_sample} candidates x 2 steps, chunk {pchunk}, oracle port (torch CPU float64)"}
+            if reference_available():
+                ref = ReferenceArm(a)
+                rrate, rdt, rchunk = cpu_rate(ref, torch.as_tensor(Xs), 2, 1)
+                cpu = {"value": rrate, "unit": "candidates/s", "cores": torch.get_num_threads(), "kind": "reference",
+                       "sample": f"{a.cpu_sample} candidates x 2 steps, chunk {rchunk}, unmodified reference "
+                                 "(baseline/_ref): GP.predict -> diagonal -> EI -> topk, torch CPU float64"}
+                if fit is not None and a.n <= 4096:
+                    ref.fit_iter()
+                    t0 = time.perf_counter()
+                    ref.fit_iter()
+                    fit["cpu_s_per_iter"] = time.perf_counter() - t0
+                    fit["cpu_kind"] = "reference (neg_log_marginal_likelihood + backward)"
+            else:
+                cpu = cpu_port
+            if fit is not None and "cpu_s_per_iter" not in fit and a.n <= 4096:
                 t0 = time.perf_counter()
-                O.objective_value_and_grad(p, Xc, yc)
+                port.fit_iter()
                 fit["cpu_s_per_iter"] = time.perf_counter() - t0
+                fit["cpu_kind"] = "port"
+            if fit is not None:
                 fit["cpu_cores"] = torch.get_num_threads()
 
     if rank == 0:
         line = {
             "metric": "EI candidates scored/sec", "value": value, "unit": "candidates/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64" if a.precision == "fp64" else "tf32",
-            "data": "synthetic",
-            "config": {"workload": workload_name(a), "n": a.n, "d": a.d, "pool_per_gpu": q, "k": TOPK,
-                       "precision": a.precision, "parallelism": f"pool sharded x{world}, 1 all-gather of top-k",
-                       "l2": "inputs larger than L2 (pool 168 MB + L^-1 134 MB per pass)"},
+            "scaling": a.scaling, "vs_baseline": None, "dtype": "f64" if a.precision == "fp64" else "tf32",
+            "data": "synthetic", "config": config_dict(a, world), "precision": a.precision,
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-            "fit": fit, "other_mode": other, "top1": {"score": float(top_s[0]), "index": int(top_i[0])},
+            "cpu_port": cpu_port, "fit": fit, "other_mode": other, "selection_matches_fp64": sel_match,
+            "refine": cert, "collective_ms": collective_ms, "state_replication_ms": state_ms,
+            "selection_matches_single_gpu": single,
+            "top": {"scores": [float(v) for v in top_s.cpu()], "indices": [int(v) for v in top_i.cpu()]},
         }
         emit_line(line)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -71,12 +71,20 @@ typedef enum bbo_status {
 typedef enum bbo_kernel_kind { BBO_KERNEL_RBF = 0, BBO_KERNEL_MATERN52 = 1 } bbo_kernel_kind;
 /* acquisitions.py:13-31 (+PI, absent from the reference) */
 typedef enum bbo_acq_kind { BBO_ACQ_EI = 0, BBO_ACQ_UCB = 1, BBO_ACQ_PI = 2 } bbo_acq_kind;
-/* arithmetic of the n^2 panel of the scoring pass */
-typedef enum bbo_precision { BBO_PREC_FP64 = 0, BBO_PREC_TF32 = 1 } bbo_precision;
+/* arithmetic of the n^2 panel of the scoring pass.
+ *   BBO_PREC_FP64         every candidate in float64 (DMMA)
+ *   BBO_PREC_TF32         every candidate on the tcgen05 TF32 panel; scores are TF32-accurate (1e-3 class)
+ *   BBO_PREC_TF32_REFINE  the TF32 pass only builds a short-list of bbo_refine_shortlist(k) candidates by TF32
+ *                         score; the short-list is re-scored by the float64 kernels and the k best BY FLOAT64
+ *                         SCORE are returned, so the returned scores are float64-exact and the selection equals
+ *                         BBO_PREC_FP64's whenever the true top-k are inside the short-list (bbo_gp_refine_info
+ *                         returns the evidence).  k <= BBO_REFINE_KMAX.                                        */
+typedef enum bbo_precision { BBO_PREC_FP64 = 0, BBO_PREC_TF32 = 1, BBO_PREC_TF32_REFINE = 2 } bbo_precision;
 
 #define BBO_ROW_ALIGN 128   /* n is padded to a multiple of this in all n x n buffers */
 #define BBO_TOPK_MAX 128
 #define BBO_APPEND_MAX 32   /* observations appended per bbo_gp_append call */
+#define BBO_REFINE_KMAX 32   /* largest k of BBO_PREC_TF32_REFINE */
 #define BBO_HOST_STAGE_CHUNKS 8   /* bbo_gp_score_pool_host copies this many chunks per H2D transfer */
 
 int bbo_version(void);
@@ -253,6 +261,19 @@ int bbo_gp_score_pool(const bbo_gp_state* st, const bbo_acq* acq, int32_t precis
                       double* var_dev, double* score_dev, int32_t* nan_count_dev,
                       void* workspace_dev, size_t workspace_bytes, int64_t q_chunk,
                       int32_t accumulate, void* stream);
+
+/* BBO_PREC_TF32_REFINE: size of the short-list kept by the TF32 pass (max(64, 8k), at most 256).        */
+int32_t bbo_refine_shortlist(int32_t k);
+/* Evidence of the last BBO_PREC_TF32_REFINE call that used this workspace (same n, d, q_chunk as that call);
+ * synchronises `stream`.  info_host[4]:
+ *   [0] k-th best float64 score returned
+ *   [1] upper bound of the TF32 score of every candidate that was NOT re-scored (-inf if all were)
+ *   [2] max |TF32 score - float64 score| over the short-list (the observed TF32 score error)
+ *   [3] number of short-listed candidates
+ * The selection provably equals the float64 mode's if no unscored candidate's float64 score can reach [0],
+ * i.e. if [0] - [1] exceeds the TF32 score error; callers compare it with a multiple of [2].              */
+int bbo_gp_refine_info(const void* workspace_dev, size_t workspace_bytes, int64_t n, int64_t d, int64_t q_chunk,
+                       double* info_host, void* stream);
 
 /* Same with the candidate pool in HOST memory (pinned for full overlap).  The pool is
  * streamed to the device in chunks of q_chunk rows on an internal copy stream, double
