@@ -2,20 +2,22 @@
 //
 //   |L^-1 k*_c|^2 = sum_i ( sum_{j<=i} Ks[c,j] * Linv[i,j] )^2          (gp.py:80-81)
 //
-// k_kstar_f32     K* in FP32 exact-difference form (kernel_impl.py:80-96), rounded to TF32 with
-//                 cvt.rna (round-to-nearest: unbiased, unlike the tensor core's own truncation),
-//                 fused with mu = c + K* alpha.
-// k_vnorm_tf32    warp-specialised tcgen05 GEMM, one CTA per SM:
-//                   warp 0   TMA producer: cp.async.bulk.tensor.2d (128B swizzle) of a 128x32 K* tile
-//                            and a 256x32 L^-1 tile per stage, 4-stage mbarrier ring (192 KB smem)
-//                   warp 1   MMA issuer: one thread, tcgen05.mma.cta_group::1.kind::tf32, M=128 (candidates)
-//                            x N=256 (rows of L^-1) x K=8, accumulators in TMEM (2 x 256 columns, double
-//                            buffered against the epilogue); tcgen05.commit releases smem stages / publishes
-//                            the accumulator
-//                   warps 2-5 epilogue: tcgen05.ld.32x32b.x32 TMEM -> registers, square + row-sum;
-//                            V = L^-1 k* is never written anywhere.
-//                 Triangular: row block nb only contracts k < (nb+1)*256.
-// SASS evidence: UTCHMMA / UTMALDG / LDTM / SYNCS (see profiles/).
+// Kernels (one default per shape; the A/B generations of round 1 were removed in round 2):
+//   K* producers (cross-covariance of a chunk, TF32-rounded float32, fused with mu = c + K* alpha)
+//     k_kstar_umma       d <= 30      tcgen05 kind::tf32, one 3xTF32 contraction over concatenated hi/lo rows,
+//                                     TMA operand loads, TMEM accumulator ring, TMA tensor stores
+//     k_kstar_mma2       30 < d <= 126  mma.sync 3xTF32 with the two augmentation columns
+//     k_kstar_f32_fast   126 < d <= 192 CUDA cores, expanded form;   k_kstar_f32  any d, exact-difference form
+//   n^2 panel (V = L^-1 k* is never written: the epilogue squares and row-sums the accumulators)
+//     k_vnorm_tf32_2sm<true>   persistent CTA pairs walking a work list (k_panel_schedule): default while the
+//                              TF32 L^-1 fits in L2 (n <= ~4500)
+//     k_vnorm_tf32_2sm<false>  one CTA pair per candidate tile pair, lock-step over the row pairs (n = 8192)
+//     k_vnorm_tf32_pair<1>     single-CTA form for chunks with an odd number of 128-candidate tiles
+//   warp roles of the panel kernels: warp 0 TMA producer (cp.async.bulk.tensor.2d, 64-byte swizzle, mbarrier
+//   ring), warp 1 one thread issuing tcgen05.mma kind::tf32 (M = 128 per CTA x N = 256 x K = 8, accumulators in
+//   TMEM, two row blocks per K* stage), warps 2-5 epilogue (tcgen05.ld.32x32b.x32 -> square + row-sum).
+//   Triangular: row block nb only contracts k < (nb+1)*256.
+// SASS evidence: UTCHMMA(.2CTA) / UTMALDG / UTMASTG / LDTM / SYNCS (see profiles/).
 #include <cuda.h>
 #include <mutex>
 #include <vector>
@@ -166,155 +168,6 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
 // vpart[split, c] = sum over this split's 256-row blocks of (Ks[c,:] . Linv[i,:])^2
 // grid (qc_pad/128, nsplit), 192 threads, 1 CTA / SM.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(tf::THREADS, 1)
-k_vnorm_tf32(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int np,
-             int64_t qc_pad, double* __restrict__ vpart) {
-  using namespace tf;
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
-  __shared__ uint32_t tmem_base_sh;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;   // 1024-byte aligned tile ring
-  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  const int c0 = blockIdx.x * BM;
-  const int nblk = (np + BN - 1) / BN;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 128);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 2) {   // TMEM allocation: one warp, all 512 columns (1 CTA per SM)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
-                 "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_sh;
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int nb = blockIdx.y; nb < nblk; nb += gridDim.y) {
-        const int kend = min((nb + 1) * BN, np);
-        for (int k = 0; k < kend; k += BK) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = sgen + stage * STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-          tma_load_2d(sa, &mapA, &full_bar[stage], k, c0);
-          tma_load_2d(sa + A_BYTES, &mapB, &full_bar[stage], k, nb * BN);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=tf32, both K-major, N=256, M=128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int nb = blockIdx.y; nb < nblk; nb += gridDim.y) {
-        const int kend = min((nb + 1) * BN, np);
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
-        for (int k = 0; k < kend; k += BK) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = sbase + stage * STAGE_BYTES;
-          const uint64_t adesc = make_desc(sa), bdesc = make_desc(sa + A_BYTES);
-#pragma unroll
-          for (int kk = 0; kk < BK / UK; ++kk) {
-            // advance 32 bytes (8 tf32) inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-            tc_mma_tf32(d_tmem, adesc + uint64_t(kk * 2), bdesc + uint64_t(kk * 2), idesc, (k | kk) != 0 ? 1u : 0u);
-          }
-          tc_commit(&empty_bar[stage]);   // frees the smem stage once these MMAs have read it
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-        tc_commit(&tfull_bar[acc]);       // accumulator complete
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
-        }
-      }
-    }
-  } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
-    const int row = quarter * 32 + lane;                // candidate row within the tile
-    // Four fixed accumulation slots (row block index mod 4): the association of a candidate's partial
-    // sums is the same whether 1, 2 or 4 CTAs share the tile, so the host may pick the split by
-    // occupancy without changing a single bit of the result.
-    double tot0 = 0.0, tot1 = 0.0, tot2 = 0.0, tot3 = 0.0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int nb = blockIdx.y; nb < nblk; nb += gridDim.y) {
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN);
-      float part = 0.f;
-#pragma unroll 2
-      for (int c = 0; c < BN; c += 32) {
-        float v[32];
-        tmem_ld32(taddr + uint32_t(c), v);
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          s0 = fmaf(v[i], v[i], s0);
-          s1 = fmaf(v[i + 1], v[i + 1], s1);
-          s2 = fmaf(v[i + 2], v[i + 2], s2);
-          s3 = fmaf(v[i + 3], v[i + 3], s3);
-        }
-        part += (s0 + s1) + (s2 + s3);
-      }
-      const int slot = nb & 3;
-      if (slot == 0) tot0 += double(part);
-      else if (slot == 1) tot1 += double(part);
-      else if (slot == 2) tot2 += double(part);
-      else tot3 += double(part);
-      tc_fence_before();
-      mbar_arrive(&tempty_bar[acc]);
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
-      }
-    }
-    // this CTA owns the slots g with g % gridDim.y == blockIdx.y (gridDim.y in {1,2,4})
-    const double tots[4] = {tot0, tot1, tot2, tot3};
-#pragma unroll
-    for (int g4 = 0; g4 < 4; ++g4)
-      if (g4 % int(gridDim.y) == int(blockIdx.y)) vpart[int64_t(g4) * qc_pad + c0 + row] = tots[g4];
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
-  }
-}
-
 // ------------------------------------------------------------------------------------------
 // Paired variant: each K* stage feeds TWO row blocks (both TMEM accumulators are live at once), so
 // the K* strip of a candidate tile is read from HBM/L2 once per PAIR of row blocks instead of once
@@ -1087,18 +940,7 @@ k_kstar_f32_fast(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const fl
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// K* on the tensor cores (TF32 mode, d <= kMmaMaxD): the scaled dot products a'.b are computed with
-// error-compensated 3xTF32 (a_hi b_hi + a_hi b_lo + a_lo b_hi, relative error ~2^-21) on
-// mma.sync.m16n8k8.tf32 (SASS HMMA.1688.F32.TF32), which removes the 20 FFMA per (candidate,
-// observation) of the CUDA-core version and leaves the exp epilogue and the store.
-//   s = |a'|^2 + |b|^2 - 2 a'.b ;  RBF: k = s2 exp(-s/2) = 2^(log2e * a'.b + A'_row + B'_col)
-// 128 candidates per CTA (8 warps x 16 rows), A fragments (hi/lo) live in registers for the whole
-// kernel, 64-observation tiles of the pre-split training set are cp.async double buffered.
-// grid (qc_pad/128), 256 threads, dynamic smem.
-// ------------------------------------------------------------------------------------------
-constexpr int kMmaMaxD = 128;
-
+// ---- tensor-core K* producers: shared helpers
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
   const float r = x - __uint_as_float(hi);
@@ -1117,161 +959,10 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// pre-split training set: Xhi/Xlo (np, dk) TF32 bit patterns of X/l, dk = 8*ceil(d/8) (zero padded)
-__global__ void __launch_bounds__(256)
-k_prescale_split(const double* __restrict__ X, int64_t n, int64_t np, int d, int dk, const double* __restrict__ hyp,
-                 const double* __restrict__ alpha, uint32_t* __restrict__ Xhi, uint32_t* __restrict__ Xlo,
-                 float* __restrict__ bnorm, float* __restrict__ alpha32) {
-  const int64_t j = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (j >= np) return;
-  float acc = 0.f;
-  for (int k = lane; k < dk; k += 32) {
-    const float v = (j < n && k < d) ? float(X[j * d + k] * hyp[d + k]) : 0.f;
-    uint32_t hi, lo;
-    split_tf32(v, hi, lo);
-    Xhi[j * dk + k] = hi;
-    Xlo[j * dk + k] = lo;
-    acc = fmaf(v, v, acc);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) {
-    bnorm[j] = acc;
-    alpha32[j] = float(alpha[j]);
-  }
-}
-
-template <typename T1, int KS>   // KS = dk / 8 k-steps
-__global__ void __launch_bounds__(256)
-k_kstar_mma(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const uint32_t* __restrict__ Xhi,
-            const uint32_t* __restrict__ Xlo, const float* __restrict__ bnorm, int64_t n, int64_t np,
-            const double* __restrict__ hyp, const float* __restrict__ alpha32, float* __restrict__ Ks,
-            double* __restrict__ mu) {
-  constexpr int DK = KS * 8;
-  constexpr int LS = 4 * ((DK / 4 + 1) | 1);   // LS/4 odd: fragment loads conflict free
-  extern __shared__ __align__(16) uint32_t msm[];
-  uint32_t* bhi = msm;                   // 2 x 64 x LS
-  uint32_t* blo = bhi + 2 * 64 * LS;     // 2 x 64 x LS
-  float* bns = reinterpret_cast<float*>(blo + 2 * 64 * LS);   // 2 x 64
-  float* als = bns + 128;                                     // 2 x 64
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int d = h.d;
-  const bool matern = h.kind == BBO_KERNEL_MATERN52;
-  const float eps = matern ? float(h.pairwise_eps) : 0.f;
-  const float s2 = float(hyp[2 * d]);
-  const float kLog2e = 1.4426950408889634f;
-  const float l2s2 = __log2f(s2);
-  const int64_t row0 = int64_t(blockIdx.x) * 128 + warp * 16;   // this warp's 16 candidates
-
-  // A fragments: a0 (g, t), a1 (g+8, t), a2 (g, t+4), a3 (g+8, t+4) per k-step; a' = xq/l - eps
-  uint32_t ahi[KS][4], alo[KS][4];
-  float an0 = 0.f, an1 = 0.f;   // |a'|^2 of rows g and g+8 (partial over this lane's k)
-#pragma unroll
-  for (int ks = 0; ks < KS; ++ks) {
-#pragma unroll
-    for (int f = 0; f < 4; ++f) {
-      const int64_t r = row0 + g + ((f & 1) ? 8 : 0);
-      const int k = ks * 8 + t + ((f & 2) ? 4 : 0);
-      float v = 0.f;
-      if (k < d) {
-        const double x = (r < qc) ? double(Xq[r * d + k]) : 0.0;
-        v = float(x * hyp[d + k]) - eps;
-      }
-      split_tf32(v, ahi[ks][f], alo[ks][f]);
-      if (f & 1) an1 = fmaf(v, v, an1);
-      else an0 = fmaf(v, v, an0);
-    }
-  }
-  an0 += __shfl_xor_sync(0xffffffffu, an0, 1);
-  an0 += __shfl_xor_sync(0xffffffffu, an0, 2);
-  an1 += __shfl_xor_sync(0xffffffffu, an1, 1);
-  an1 += __shfl_xor_sync(0xffffffffu, an1, 2);
-  const float Ap0 = fmaf(-0.5f * kLog2e, an0, l2s2), Ap1 = fmaf(-0.5f * kLog2e, an1, l2s2);
-
-  auto tload = [&](int64_t j0, int buf) {
-    // 64 rows x DK words, 16-byte chunks, both arrays
-    constexpr int CH = DK / 4;
-    for (int c = tid; c < 64 * CH * 2; c += 256) {
-      const int arr = c / (64 * CH), rem = c % (64 * CH), r = rem / CH, ch = rem % CH;
-      const uint32_t* src = (arr ? Xlo : Xhi) + (j0 + r) * DK + ch * 4;
-      uint32_t* dst = (arr ? blo : bhi) + (buf * 64 + r) * LS + ch * 4;
-      const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(dst));
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src));
-    }
-    if (tid < 64) {
-      bns[buf * 64 + tid] = bnorm[j0 + tid];
-      als[buf * 64 + tid] = alpha32[j0 + tid];
-    }
-    asm volatile("cp.async.commit_group;");
-  };
-  tload(0, 0);
-  float m0 = 0.f, m1 = 0.f;   // mu partials of rows g, g+8
-  const int ntile = int(np / 64);
-  float* out0 = Ks + (row0 + g) * np;
-  float* out1 = Ks + (row0 + g + 8) * np;
-  for (int tl = 0; tl < ntile; ++tl) {
-    const int buf = tl & 1;
-    const int64_t j0 = int64_t(tl) * 64;
-    asm volatile("cp.async.wait_group 0;");
-    __syncthreads();                                   // tile tl visible; everyone is done with tile tl-1
-    if (tl + 1 < ntile) tload(j0 + 64, buf ^ 1);
-    const uint32_t* ph = bhi + buf * 64 * LS;
-    const uint32_t* pl = blo + buf * 64 * LS;
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      float c[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        const int o = (nt * 8 + g) * LS + ks * 8 + t;   // b0 (k=t, n=g), b1 (k=t+4, n=g)
-        const uint32_t h0 = ph[o], h1 = ph[o + 4], l0 = pl[o], l1 = pl[o + 4];
-        mma_tf32_16x8x8(c, alo[ks], h0, h1);
-        mma_tf32_16x8x8(c, ahi[ks], l0, l1);
-        mma_tf32_16x8x8(c, ahi[ks], h0, h1);
-      }
-      const int cl = nt * 8 + 2 * t;
-      const int64_t j = j0 + cl;
-      const float bn0 = bns[buf * 64 + cl], bn1 = bns[buf * 64 + cl + 1];
-      const float al0 = als[buf * 64 + cl], al1 = als[buf * 64 + cl + 1];
-      float v[4];
-      if (!matern) {
-        const float B0 = -0.5f * kLog2e * bn0, B1 = -0.5f * kLog2e * bn1;
-        v[0] = exp2f(fminf(fmaf(c[0], kLog2e, Ap0 + B0), l2s2));
-        v[1] = exp2f(fminf(fmaf(c[1], kLog2e, Ap0 + B1), l2s2));
-        v[2] = exp2f(fminf(fmaf(c[2], kLog2e, Ap1 + B0), l2s2));
-        v[3] = exp2f(fminf(fmaf(c[3], kLog2e, Ap1 + B1), l2s2));
-      } else {
-        const float sq[4] = {fmaf(-2.f, c[0], an0 + bn0), fmaf(-2.f, c[1], an0 + bn1),
-                             fmaf(-2.f, c[2], an1 + bn0), fmaf(-2.f, c[3], an1 + bn1)};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float r = 2.2360679775f * sqrtf(fmaxf(sq[e], 0.f));
-          v[e] = s2 * (1.f + r + r * r * (1.f / 3.f)) * __expf(-r);
-        }
-      }
-      if (j >= n) v[0] = v[2] = 0.f;
-      if (j + 1 >= n) v[1] = v[3] = 0.f;
-      m0 = fmaf(v[0], al0, fmaf(v[1], al1, m0));
-      m1 = fmaf(v[2], al0, fmaf(v[3], al1, m1));
-      uint32_t u[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) u[e] = round_tf32_bits(v[e]);
-      *reinterpret_cast<uint2*>(out0 + j) = make_uint2(u[0], u[1]);
-      *reinterpret_cast<uint2*>(out1 + j) = make_uint2(u[2], u[3]);
-    }
-  }
-  m0 += __shfl_xor_sync(0xffffffffu, m0, 1);
-  m0 += __shfl_xor_sync(0xffffffffu, m0, 2);
-  m1 += __shfl_xor_sync(0xffffffffu, m1, 1);
-  m1 += __shfl_xor_sync(0xffffffffu, m1, 2);
-  if (t == 0) {
-    mu[row0 + g] = hyp[2 * d + 1] + double(m0);
-    mu[row0 + g + 8] = hyp[2 * d + 1] + double(m1);
-  }
-}
-
 // ------------------------------------------------------------------------------------------
-// K* producer, second form (default).  Same 3xTF32 mma.sync contraction, but the contraction is
+// K* producer on mma.sync (default for 30 < d <= 126; d <= 30 uses the tcgen05 producer k_kstar_umma below).
+// The scaled dot products a'.b are computed with error-compensated 3xTF32 (a_hi b_hi + a_hi b_lo + a_lo b_hi,
+// relative error ~2^-21) on mma.sync.m16n8k8.tf32 (SASS HMMA.1688.F32.TF32); the contraction is
 // AUGMENTED by two columns so that the tensor core returns the finished exponent / distance:
 //   RBF     a = [log2e * a', A', 1, 0..]   b = [b, 1, B', 0..]   a.b = log2(s2) - log2e/2 |a'-b|^2
 //           with A' = log2(s2) - log2e/2 |a'|^2, B' = -log2e/2 |b|^2        ->  k = ex2(a.b)
@@ -1281,21 +972,8 @@ k_kstar_mma(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const uint32_
 // B fragments come from ldmatrix.x4 (hi/lo x two k-halves per instruction; the b16 view of a row of
 // four 32-bit words hands lane (g,t) word t of row g, which is the tf32 B fragment), ex2 is the bare
 // MUFU.  Per 16x8 output tile: 3*KS HMMA + KS LDSM + 1 LDS.64 + 4 MUFU + 4 CVT + 4 FFMA + 2 STG.64
-// (the first form issued ~110 instructions per tile; ncu in profiles/).
 // ------------------------------------------------------------------------------------------
 constexpr int kMma2MaxD = 126;
-constexpr int kMma3MaxD = 46;    // third form: KS <= 6 (the B fragments of 4-8 candidate groups live in registers)
-// Measured (d = 20): third form 0.185 ms vs second form 0.205 ms per 37888 x 4096 values, but 0.243 vs 0.226
-// at n = 1024 (only 8 pipeline iterations per CTA against a fixed per-CTA set-up).  It is the default where it
-// has been measured faster: KS <= 3 (d <= 22) and np >= 2048; BBO_KSTAR_V3=1 forces it for every d <= 46.
-static bool use_kstar_v3(int d, int64_t np) {
-  static const bool v1 = getenv("BBO_KSTAR_V1") != nullptr, v2 = getenv("BBO_KSTAR_V2") != nullptr;
-  static const bool force = getenv("BBO_KSTAR_V3") != nullptr;
-  static const bool no_mma = getenv("BBO_KSTAR_NO_MMA") != nullptr;
-  if (v1 || v2 || no_mma || d > kMma3MaxD) return false;
-  return force || (d <= 22 && np >= 2048);
-}
-
 __global__ void __launch_bounds__(256)
 k_prescale_aug(const double* __restrict__ X, int64_t n, int64_t np, int d, int dk, int matern,
                const double* __restrict__ hyp, const double* __restrict__ alpha, uint32_t* __restrict__ Xhi,
@@ -1466,269 +1144,17 @@ k_kstar_mma2(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const uint32
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// K* producer, third form (default for d <= 46): the same augmented 3xTF32 contraction with the ROLES
-// SWAPPED -- the training set is the 16-row A operand, streamed straight from L2 in fragment order
-// (k_prescale_frag lays it out so that one LDG.128 per lane is one A fragment), and the candidates are the
-// 8-column B operand, G groups of 8 candidates resident in registers for the whole kernel.
-//   * one A tile (6 LDG.128 at d = 20) feeds G*3*KS MMAs: 1 load per 12 MMAs instead of 1 LDSM per 3;
-//   * no shared-memory staging, no CTA barrier in the main loop: each of the 8 warps of a CTA walks its
-//     own interleaved share of the observation tiles (tile = 8*it + warp) with the next tile's fragments
-//     prefetched, and G independent accumulator chains per warp hide the MMA / MUFU latency;
-//   * mu = c + K* alpha: per-lane partials over the observation rows it owns, reduced over the row lanes
-//     by shuffles and over the 8 warps through shared memory in a fixed order (deterministic).
-// CTA = 8*G candidates x all observations; grid = qc_pad / (8*G).
-// Fragment layout (uint32): Afrag[((tile*KS + ks)*2 + hl)*128 + lane*4 + f], hl 0 = hi, 1 = lo,
-//   f: a0 (g, t), a1 (g+8, t), a2 (g, t+4), a3 (g+8, t+4) of the 16 x 8 slab (tile, ks).
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_prescale_frag(const double* __restrict__ X, int64_t n, int64_t np, int d, int ks_n, int matern,
-                const double* __restrict__ hyp, const double* __restrict__ alpha, uint32_t* __restrict__ Afrag,
-                float* __restrict__ alpha32) {
-  // one warp per observation: the row's augmented vector, then scattered into fragment order
-  const int64_t j = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (j >= np) return;
-  const int dk = ks_n * 8;
-  float acc = 0.f;
-  for (int k = lane; k < d; k += 32) {
-    const float v = (j < n) ? float(X[j * d + k] * hyp[d + k]) : 0.f;
-    acc = fmaf(v, v, acc);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  const int64_t tile = j >> 4;
-  const int r = int(j & 15), g = r & 7, up = r >> 3;         // row within the tile: a0/a2 (g) or a1/a3 (g+8)
-  for (int k = lane; k < dk; k += 32) {
-    float v = 0.f;
-    if (k < d) v = (j < n) ? float(X[j * d + k] * hyp[d + k]) : 0.f;
-    else if (k == d) v = 1.f;
-    else if (k == d + 1) v = (j < n) ? (matern ? acc : -0.5f * 1.4426950408889634f * acc) : (matern ? 1e8f : -1e4f);
-    uint32_t hi, lo;
-    split_tf32(v, hi, lo);
-    const int ks = k >> 3, kc = k & 7, t = kc & 3, f = up + 2 * (kc >> 2);
-    const int64_t base = ((tile * ks_n + ks) * 2) * 128 + (g * 4 + t) * 4 + f;
-    Afrag[base] = hi;
-    Afrag[base + 128] = lo;
-  }
-  if (lane == 0) alpha32[j] = (j < n) ? float(alpha[j]) : 0.f;
-}
-
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(tf::smem_u32(dst)), "l"(src), "r"(bytes), "r"(tf::smem_u32(bar))
                : "memory");
 }
 
-// Candidate vectors of one chunk in B-fragment order (one warp per candidate), so that k_kstar_mma3 starts
-// with 2*KS coalesced 8-byte loads per lane instead of building the vectors per CTA:
-//   u = [log2e a', A', 1, 0..] (RBF)  |  [-2 a', |a'|^2, 1, 0..] (Matern),  a' = xq / l - eps
-//   Bfrag[((grp*KS + ks)*2 + hl)*64 + (g*4 + t)*2 + f]: candidate 8 grp + g, element 8 ks + t + 4 f.
-template <typename T1>
-__global__ void __launch_bounds__(256)
-k_prescale_cand(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, int64_t qc_pad, int ks_n,
-                const double* __restrict__ hyp, uint32_t* __restrict__ Bfrag) {
-  const int64_t c = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (c >= qc_pad) return;
-  const int d = h.d, dk = ks_n * 8;
-  const bool matern = h.kind == BBO_KERNEL_MATERN52;
-  const float eps = matern ? float(h.pairwise_eps) : 0.f;
-  const float kLog2e = 1.4426950408889634f;
-  float an = 0.f;
-  for (int k = lane; k < d; k += 32) {
-    const double x = (c < qc) ? double(Xq[c * d + k]) : 0.0;
-    const float v = float(x * hyp[d + k]) - eps;
-    an = fmaf(v, v, an);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) an += __shfl_xor_sync(0xffffffffu, an, o);
-  const float R = matern ? an : fmaf(-0.5f * kLog2e, an, __log2f(float(hyp[2 * d])));
-  const int64_t grp = c >> 3;
-  const int g = int(c & 7);
-  for (int k = lane; k < dk; k += 32) {
-    float u = 0.f;
-    if (k < d) {
-      const double x = (c < qc) ? double(Xq[c * d + k]) : 0.0;
-      u = (matern ? -2.f : kLog2e) * (float(x * hyp[d + k]) - eps);
-    } else if (k == d) {
-      u = R;
-    } else if (k == d + 1) {
-      u = 1.f;
-    }
-    uint32_t hi, lo;
-    split_tf32(u, hi, lo);
-    const int ks = k >> 3, kc = k & 7, t = kc & 3, f = kc >> 2;
-    const int64_t base = ((grp * ks_n + ks) * 2) * 64 + (g * 4 + t) * 2 + f;
-    Bfrag[base] = hi;
-    Bfrag[base + 64] = lo;
-  }
-}
-
-template <int KS>
-struct Kstar3Cfg {
-  static constexpr int kTileBytes = KS * 2 * 512;              // one 16-observation tile, hi + lo fragments
-  static constexpr int kStageBytes = 8 * kTileBytes + 512;     // 8 tiles (one per warp) + 128 alpha values
-  static constexpr int kStages = 3;
-  static constexpr size_t kSmem = size_t(kStages) * kStageBytes + 2 * kStages * sizeof(uint64_t);
-};
-
-template <int KS, int G, bool MATERN>
-__global__ void __launch_bounds__(256, (G * KS <= 12) ? 2 : 1)
-k_kstar_mma3(bbo_gp_hyper h, const uint32_t* __restrict__ Bfrag, const uint32_t* __restrict__ Afrag,
-             int64_t np, const double* __restrict__ hyp, const float* __restrict__ alpha32,
-             float* __restrict__ Ks, double* __restrict__ mu) {
-  using Cfg = Kstar3Cfg<KS>;
-  extern __shared__ __align__(128) unsigned char k3_sm[];
-  __shared__ float red[8][8 * G];
-  uint64_t* full = reinterpret_cast<uint64_t*>(k3_sm + size_t(Cfg::kStages) * Cfg::kStageBytes);
-  uint64_t* empty = full + Cfg::kStages;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int d = h.d;
-  const float s2 = float(hyp[2 * d]);
-  const float kLog2e = 1.4426950408889634f;
-  const float l2s2 = __log2f(s2);
-  const int64_t cand0 = int64_t(blockIdx.x) * (8 * G);
-  const int niter = int(np / 128);                          // 8 tiles of 16 observations per iteration
-
-  // ---- TMA producer (thread 0): one bulk copy of the 8 fragment-ordered tiles + one of the alpha slice
-  // per stage, completion on the stage's "full" mbarrier; a stage is refilled once all 8 warps have
-  // arrived on its "empty" mbarrier (they do as soon as their fragments are in registers).
-  auto produce = [&](int it) {
-    const int st = it % Cfg::kStages;
-    unsigned char* dst = k3_sm + size_t(st) * Cfg::kStageBytes;
-    tf::mbar_expect_tx(&full[st], uint32_t(Cfg::kStageBytes));
-    bulk_g2s(dst, reinterpret_cast<const unsigned char*>(Afrag) + size_t(it) * 8 * Cfg::kTileBytes,
-             uint32_t(8 * Cfg::kTileBytes), &full[st]);
-    bulk_g2s(dst + 8 * Cfg::kTileBytes, alpha32 + size_t(it) * 128, 512u, &full[st]);
-  };
-  if (tid == 0) {
-    for (int st = 0; st < Cfg::kStages; ++st) {
-      tf::mbar_init(&full[st], 1);
-      tf::mbar_init(&empty[st], 8);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (tid == 0)
-    for (int it = 0; it < Cfg::kStages - 1 && it < niter; ++it) produce(it);
-
-  // ---- B fragments (candidate cand0 + 8*grp + g, elements k = 8 ks + t and 8 ks + t + 4), prepared in
-  // fragment order by k_prescale_cand: 2 KS coalesced 8-byte loads per group and lane
-  uint32_t bhi[G][KS][2], blo[G][KS][2];
-  {
-    const uint2* bf = reinterpret_cast<const uint2*>(Bfrag) + (int64_t(blockIdx.x) * G * KS * 2) * 32 + lane;
-#pragma unroll
-    for (int grp = 0; grp < G; ++grp)
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        const uint2 hv = __ldg(bf + ((grp * KS + ks) * 2) * 32);
-        const uint2 lv = __ldg(bf + ((grp * KS + ks) * 2 + 1) * 32);
-        bhi[grp][ks][0] = hv.x;
-        bhi[grp][ks][1] = hv.y;
-        blo[grp][ks][0] = lv.x;
-        blo[grp][ks][1] = lv.y;
-      }
-  }
-
-  float m[G][2];
-#pragma unroll
-  for (int grp = 0; grp < G; ++grp) m[grp][0] = m[grp][1] = 0.f;
-  for (int it = 0; it < niter; ++it) {
-    const int st = it % Cfg::kStages;
-    const uint32_t par = uint32_t(it / Cfg::kStages) & 1u;
-    if (tid == 0) {          // keep kStages - 1 iterations in flight: refill the stage read one iteration ago
-      const int nx = it + Cfg::kStages - 1;
-      if (nx < niter) {
-        if (nx >= Cfg::kStages) tf::mbar_wait(&empty[nx % Cfg::kStages], uint32_t(nx / Cfg::kStages - 1) & 1u);
-        produce(nx);
-      }
-    }
-    __syncwarp();
-    tf::mbar_wait(&full[st], par);
-    const unsigned char* stage = k3_sm + size_t(st) * Cfg::kStageBytes;
-    const uint4* fr = reinterpret_cast<const uint4*>(stage + warp * Cfg::kTileBytes) + lane;
-    uint4 a_cur[KS][2];
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-      a_cur[ks][0] = fr[(ks * 2) * 32];
-      a_cur[ks][1] = fr[(ks * 2 + 1) * 32];
-    }
-    const float* als = reinterpret_cast<const float*>(stage + 8 * Cfg::kTileBytes) + warp * 16;
-    const float al0 = als[g], al1 = als[g + 8];
-    __syncwarp();
-    if (lane == 0) tf::mbar_arrive(&empty[st]);
-    const int64_t tile = int64_t(it) * 8 + warp;
-    float* out = Ks + (cand0 + 2 * t) * np + tile * 16 + g;
-    // four candidate groups at a time: consecutive MMAs belong to four independent accumulator chains
-#pragma unroll
-    for (int g4 = 0; g4 < G; g4 += 4) {
-      float c[4][4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        const uint32_t (&ah)[4] = reinterpret_cast<const uint32_t (&)[4]>(a_cur[ks][0]);
-        const uint32_t (&alw)[4] = reinterpret_cast<const uint32_t (&)[4]>(a_cur[ks][1]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) mma_tf32_16x8x8(c[j], alw, bhi[g4 + j][ks][0], bhi[g4 + j][ks][1]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) mma_tf32_16x8x8(c[j], ah, blo[g4 + j][ks][0], blo[g4 + j][ks][1]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) mma_tf32_16x8x8(c[j], ah, bhi[g4 + j][ks][0], bhi[g4 + j][ks][1]);
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int grp = g4 + j;
-        float v[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if (!MATERN) {
-            v[e] = ex2_approx(fminf(c[j][e], l2s2));
-          } else {
-            const float r = 2.2360679775f * sqrtf(fmaxf(c[j][e], 0.f));
-            v[e] = s2 * fmaf(r, fmaf(r, 1.f / 3.f, 1.f), 1.f) * ex2_approx(-kLog2e * r);
-          }
-        }
-        // c0 (obs g, cand 2t), c1 (obs g, cand 2t+1), c2 (obs g+8, cand 2t), c3 (obs g+8, cand 2t+1)
-        m[grp][0] = fmaf(v[0], al0, fmaf(v[2], al1, m[grp][0]));
-        m[grp][1] = fmaf(v[1], al0, fmaf(v[3], al1, m[grp][1]));
-        uint32_t u[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) u[e] = round_tf32_bits(v[e]);
-        float* o = out + int64_t(8 * grp) * np;
-        reinterpret_cast<uint32_t*>(o)[0] = u[0];
-        reinterpret_cast<uint32_t*>(o + np)[0] = u[1];
-        reinterpret_cast<uint32_t*>(o)[8] = u[2];
-        reinterpret_cast<uint32_t*>(o + np)[8] = u[3];
-      }
-    }
-  }
-  // mu: sum over the observation rows (lane bits 2..4), then over the 8 warps in a fixed order
-#pragma unroll
-  for (int grp = 0; grp < G; ++grp)
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      float x = m[grp][e];
-      x += __shfl_xor_sync(0xffffffffu, x, 4);
-      x += __shfl_xor_sync(0xffffffffu, x, 8);
-      x += __shfl_xor_sync(0xffffffffu, x, 16);
-      if (g == 0) red[warp][8 * grp + 2 * t + e] = x;
-    }
-  __syncthreads();
-  if (tid < 8 * G) {
-    float x = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) x += red[w][tid];
-    mu[cand0 + tid] = hyp[2 * d + 1] + double(x);
-  }
-}
-
 // ------------------------------------------------------------------------------------------
-// K* producer, fourth form (default for d <= 30): the augmented 3xTF32 contraction of the second form on
-// the tcgen05 tensor cores.  The three partial products are ONE contraction of length 3 dk over
+// K* producer on tcgen05 (default for d <= 30): the augmented 3xTF32 contraction of k_kstar_mma2 on
+// the 5th-generation tensor cores.  The three partial products are ONE contraction of length 3 dk over
 // concatenated operand rows,
-//     candidates   Aop[c] = [ hi(u) | hi(u) | lo(u) | 0.. ]      u as in k_prescale_cand
+//     candidates   Aop[c] = [ hi(u) | hi(u) | lo(u) | 0.. ]      u = the augmented candidate row of k_kstar_mma2
 //     observations Bop[j] = [ hi(b) | lo(b) | hi(b) | 0.. ]      b as in k_prescale_aug
 // so Aop[c] . Bop[j] = u_hi b_hi + u_hi b_lo + u_lo b_hi is the finished exponent (RBF) / squared distance
 // (Matern).  Persistent CTAs (one per SM), 576 threads, warp specialised:
@@ -2047,13 +1473,6 @@ static size_t kstar_mma2_smem() {
   constexpr int DK = KS * 8, LS = 4 * ((DK / 4 + 1) | 1);
   return sizeof(uint32_t) * (size_t(4) * 64 * LS) + sizeof(float) * 128;
 }
-
-template <int KS>
-static size_t kstar_mma_smem() {
-  constexpr int DK = KS * 8, LS = 4 * ((DK / 4 + 1) | 1);
-  return sizeof(uint32_t) * (size_t(4) * 64 * LS) + sizeof(float) * 256;
-}
-
 constexpr int kFastMaxD = 192;
 static size_t kstar_fast_smem(int d) {
   const int LS = 4 * ((((d + 3) / 4) + 1) | 1);
@@ -2233,12 +1652,10 @@ static int get_aux(Tf32Aux** out) {
   return BBO_OK;
 }
 
-// fourth K* form (tcgen05): default for d <= 30; BBO_KSTAR_NO_UMMA=1 or any of the BBO_KSTAR_V1/V2/V3 /
-// BBO_KSTAR_NO_MMA switches fall back to the mma.sync / CUDA-core forms
+// tcgen05 K* producer: default for d <= 30.  BBO_KSTAR_NO_UMMA=1 sends those shapes through k_kstar_mma2 (the
+// default for 30 < d <= 126) -- used by the test that checks both producers give the same selection.
 static bool use_kstar_umma(int d) {
-  static const bool off = getenv("BBO_KSTAR_NO_UMMA") != nullptr || getenv("BBO_KSTAR_V1") != nullptr ||
-                          getenv("BBO_KSTAR_V2") != nullptr || getenv("BBO_KSTAR_V3") != nullptr ||
-                          getenv("BBO_KSTAR_NO_MMA") != nullptr;
+  static const bool off = getenv("BBO_KSTAR_NO_UMMA") != nullptr;
   return !off && d <= ku::kMaxD;
 }
 static int sm_count() {
@@ -2254,9 +1671,6 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
                         const void* Xq, int xq_is_f32, int64_t qc, int64_t qc_pad, double* mu_chunk, cudaStream_t st) {
   const int64_t np = w.np;
   prof_begin(kProfKstar, st);
-  static const bool use_mma = getenv("BBO_KSTAR_NO_MMA") == nullptr;
-  static const bool use_v1 = getenv("BBO_KSTAR_V1") != nullptr;
-  static const bool use_v2 = getenv("BBO_KSTAR_V2") != nullptr;
   if (use_kstar_umma(s.h.d)) {
     const int dk = 8 * ((s.h.d + 2 + 7) / 8), ktp = 32 * ((3 * dk + 31) / 32), nbox = ktp / 32;
     const bool matern = s.h.kind == BBO_KERNEL_MATERN52;
@@ -2291,45 +1705,7 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
     else
       k_kstar_umma<false><<<unsigned(grid), ku::THREADS, sm, st>>>(mapA, mapB, mapO, int(np), tiles, nbox, 3 * dk / 8,
                                                                   s.h.d, hyp, t.alpha32, mu_chunk);
-  } else if (use_kstar_v3(s.h.d, np)) {
-    const int ks = (s.h.d + 2 + 7) / 8;
-    const bool matern = s.h.kind == BBO_KERNEL_MATERN52;
-    if (xq_is_f32)
-      k_prescale_cand<float><<<unsigned(qc_pad / 8), 256, 0, st>>>(s.h, static_cast<const float*>(Xq), qc, qc_pad, ks,
-                                                                  s.hyp, t.Bfrag);
-    else
-      k_prescale_cand<double><<<unsigned(qc_pad / 8), 256, 0, st>>>(s.h, static_cast<const double*>(Xq), qc, qc_pad,
-                                                                   ks, s.hyp, t.Bfrag);
-    BBO_LAUNCH_CHECK();
-#define BBO_KSTAR_MMA3_L(KS_, G_, M_)                                                                           \
-  k_kstar_mma3<KS_, G_, M_><<<unsigned(qc_pad / (8 * G_)), 256, Kstar3Cfg<KS_>::kSmem, st>>>(                   \
-      s.h, t.Bfrag, t.Xhi, np, s.hyp, t.alpha32, t.Ks[buf], mu_chunk)
-#define BBO_KSTAR_MMA3(KS_, G_)                                                                                 \
-  case KS_: {                                                                                                   \
-    static DeviceOnce attr_once;                                                                                \
-    if (attr_once.first()) {                                                                                    \
-      const int sm = int(Kstar3Cfg<KS_>::kSmem);                                                                \
-      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_mma3<KS_, G_, false>,                                         \
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, sm));                    \
-      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_mma3<KS_, G_, true>,                                          \
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, sm));                    \
-    }                                                                                                           \
-    if (matern) BBO_KSTAR_MMA3_L(KS_, G_, true);                                                                \
-    else BBO_KSTAR_MMA3_L(KS_, G_, false);                                                                      \
-  } break;
-    switch (ks) {
-      BBO_KSTAR_MMA3(1, 8)
-      BBO_KSTAR_MMA3(2, 4)
-      BBO_KSTAR_MMA3(3, 4)
-      BBO_KSTAR_MMA3(4, 4)
-      BBO_KSTAR_MMA3(5, 4)
-      BBO_KSTAR_MMA3(6, 4)
-      default:
-        return BBO_ERR_BAD_ARG;
-    }
-#undef BBO_KSTAR_MMA3
-#undef BBO_KSTAR_MMA3_L
-  } else if (use_mma && !use_v1 && s.h.d <= kMma2MaxD) {
+  } else if (s.h.d <= kMma2MaxD) {
     const int ks = (s.h.d + 2 + 7) / 8;
     const unsigned grid = unsigned(qc_pad / 128);
     const bool matern = s.h.kind == BBO_KERNEL_MATERN52;
@@ -2380,47 +1756,6 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
     }
 #undef BBO_KSTAR_MMA2
 #undef BBO_KSTAR_MMA2_L
-  } else if (use_mma && s.h.d <= kMmaMaxD) {
-    const int ks = (s.h.d + 7) / 8;
-    const unsigned grid = unsigned(qc_pad / 128);
-#define BBO_KSTAR_MMA(KS_)                                                                                     \
-  case KS_: {                                                                                                  \
-    const size_t sm = kstar_mma_smem<KS_>();                                                                   \
-    static DeviceOnce attr_once;                                                                               \
-    if (sm > 48 * 1024 && attr_once.first()) {                                                                 \
-      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_mma<float, KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          int(sm)));                                                           \
-      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_mma<double, KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          int(sm)));                                                           \
-    }                                                                                                          \
-    if (xq_is_f32)                                                                                             \
-      k_kstar_mma<float, KS_><<<grid, 256, sm, st>>>(s.h, static_cast<const float*>(Xq), qc, t.Xhi, t.Xlo,      \
-                                                     t.bnorm, s.n, np, s.hyp, t.alpha32, t.Ks[buf], mu_chunk);  \
-    else                                                                                                       \
-      k_kstar_mma<double, KS_><<<grid, 256, sm, st>>>(s.h, static_cast<const double*>(Xq), qc, t.Xhi, t.Xlo,    \
-                                                      t.bnorm, s.n, np, s.hyp, t.alpha32, t.Ks[buf], mu_chunk); \
-  } break;
-    switch (ks) {
-      BBO_KSTAR_MMA(1)
-      BBO_KSTAR_MMA(2)
-      BBO_KSTAR_MMA(3)
-      BBO_KSTAR_MMA(4)
-      BBO_KSTAR_MMA(5)
-      BBO_KSTAR_MMA(6)
-      BBO_KSTAR_MMA(7)
-      BBO_KSTAR_MMA(8)
-      BBO_KSTAR_MMA(9)
-      BBO_KSTAR_MMA(10)
-      BBO_KSTAR_MMA(11)
-      BBO_KSTAR_MMA(12)
-      BBO_KSTAR_MMA(13)
-      BBO_KSTAR_MMA(14)
-      BBO_KSTAR_MMA(15)
-      BBO_KSTAR_MMA(16)
-      default:
-        return BBO_ERR_BAD_ARG;
-    }
-#undef BBO_KSTAR_MMA
   } else if (s.h.d <= kFastMaxD) {
     static DeviceOnce fast_attr_once;
     const size_t ksm = kstar_fast_smem(s.h.d);
@@ -2455,18 +1790,14 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
 // four fixed slots of `vpart`; -nblk = one slot per row block in the persistent panel's own buffer).
 static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf32Scratch& t, int buf,
                         int64_t qc_pad, double* vpart, int* nsplit_out, double** vpart_out, cudaStream_t st) {
-  static DeviceOnce attr_once;
-  if (attr_once.first())
-    BBO_CUDA_CHECK(cudaFuncSetAttribute(k_vnorm_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, tf::SMEM_BYTES));
   const int64_t np = w.np;
-  static const bool pair = getenv("BBO_TF32_SINGLE") == nullptr;    // paired row blocks by default
-  static const bool clus = getenv("BBO_TF32_NO_CLUSTER") == nullptr; // 2-CTA clusters
-  static const bool two_sm = getenv("BBO_TF32_NO_2SM") == nullptr;   // cta_group::2 MMA (else TMA multicast)
+  // chunks with an even number of 128-candidate tiles run on CTA pairs (cta_group::2); BBO_TF32_NO_CLUSTER=1 sends
+  // every chunk through the single-CTA kernel that otherwise serves odd tile counts (same bits: tests compare them)
+  static const bool clus = getenv("BBO_TF32_NO_CLUSTER") == nullptr;
+  constexpr bool pair = true, two_sm = true;
   static DeviceOnce attr2_once;
-  if (pair && attr2_once.first()) {
+  if (attr2_once.first()) {
     BBO_CUDA_CHECK(cudaFuncSetAttribute(k_vnorm_tf32_pair<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        tfp::SMEM_BYTES));
-    BBO_CUDA_CHECK(cudaFuncSetAttribute(k_vnorm_tf32_pair<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         tfp::SMEM_BYTES));
     BBO_CUDA_CHECK(cudaFuncSetAttribute(k_vnorm_tf32_2sm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         tf2::SMEM_BYTES));
@@ -2559,17 +1890,12 @@ static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
       }
       *nsplit_out = -int(nblk);
       *vpart_out = vp32;
-    } else if (two_sm)
+    } else
       BBO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_vnorm_tf32_2sm<false>, mapA, mapB, np_i, qp_i, vp, shrink,
                                         static_cast<const int*>(nullptr), 0));
-    else
-      BBO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_vnorm_tf32_pair<2>, mapA, mapB, np_i, qp_i, vp));
-  } else if (pair)
+  } else
     k_vnorm_tf32_pair<1><<<dim3(unsigned(tiles), unsigned(nsplit)), tf::THREADS, tfp::SMEM_BYTES, st>>>(
         mapA, mapB, int(np), w.qp, vpart);
-  else
-    k_vnorm_tf32<<<dim3(unsigned(tiles), unsigned(nsplit)), tf::THREADS, tf::SMEM_BYTES, st>>>(mapA, mapB, int(np),
-                                                                                              w.qp, vpart);
   BBO_LAUNCH_CHECK();
   prof_end(kProfTf32, st);
   return BBO_OK;
@@ -2606,31 +1932,17 @@ int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const vo
   const Tf32Scratch t = carve(w, s.h.d);
   const size_t esz = xq_is_f32 ? sizeof(float) : sizeof(double);
   const int d = s.h.d;
-  static const bool use_mma = getenv("BBO_KSTAR_NO_MMA") == nullptr;
-  static const bool use_v1 = getenv("BBO_KSTAR_V1") != nullptr;
-  static const bool use_v2 = getenv("BBO_KSTAR_V2") != nullptr;
   if (use_kstar_umma(d)) {
     const int dk = 8 * ((d + 2 + 7) / 8), ktp = 32 * ((3 * dk + 31) / 32);
     k_prescale_aug_umma<<<unsigned(ceil_div(w.np, 8)), 256, 0, st>>>(s.X, s.n, w.np, d, dk, ktp,
                                                                     s.h.kind == BBO_KERNEL_MATERN52 ? 1 : 0, s.hyp,
                                                                     s.alpha, t.Bop, t.alpha32);
     BBO_LAUNCH_CHECK();
-  } else if (use_kstar_v3(d, w.np)) {
-    // fragment-ordered training set: uses the Xhi and Xlo regions back to back (2 np DK words <= both)
-    k_prescale_frag<<<unsigned(ceil_div(w.np, 8)), 256, 0, st>>>(s.X, s.n, w.np, d, (d + 2 + 7) / 8,
-                                                                s.h.kind == BBO_KERNEL_MATERN52 ? 1 : 0, s.hyp, s.alpha,
-                                                                t.Xhi, t.alpha32);
-    BBO_LAUNCH_CHECK();
-  } else if (use_mma && !use_v1 && d <= kMma2MaxD) {
+  } else if (d <= kMma2MaxD) {
     const int dk = 8 * ((d + 2 + 7) / 8);
     k_prescale_aug<<<unsigned(ceil_div(w.np, 8)), 256, 0, st>>>(s.X, s.n, w.np, d, dk,
                                                                s.h.kind == BBO_KERNEL_MATERN52 ? 1 : 0, s.hyp, s.alpha,
                                                                t.Xhi, t.Xlo, t.alpha32);
-    BBO_LAUNCH_CHECK();
-  } else if (use_mma && d <= kMmaMaxD) {
-    const int dk = 8 * ((d + 7) / 8);
-    k_prescale_split<<<unsigned(ceil_div(w.np, 8)), 256, 0, st>>>(s.X, s.n, w.np, d, dk, s.hyp, s.alpha, t.Xhi, t.Xlo,
-                                                                 t.bnorm, t.alpha32);
     BBO_LAUNCH_CHECK();
   } else if (d <= kFastMaxD) {
     k_prescale<<<unsigned(ceil_div(w.np, 8)), 256, 0, st>>>(s.X, s.n, w.np, d, s.hyp, s.alpha, t.Xs, t.bnorm,
