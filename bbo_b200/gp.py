@@ -422,14 +422,33 @@ class CudaGP(Surrogate):
         Xq: (q,d) float64/float32; a CUDA tensor, or (``host_pool=True``) a CPU tensor that is streamed
         to the device in chunks overlapped with the kernels.  ``acq`` is an EI/UCB/PI from
         ``bbo_b200.acquisitions``.  Returns (scores[k] f64, indices[k] i64[, mu, var, score]).
-        ``running`` = (scores, indices) from a previous call to merge with (pool sharded in time)."""
+        ``running`` = (scores, indices) from a previous call to merge with (pool sharded in time).
+        ``precision``: "fp64" | "tf32" | "tf32+refine" (TF32 short-list, float64 re-score and selection) | "auto"
+        (tf32+refine when its evidence certifies the float64 selection, float64 otherwise; synchronises)."""
         from .acquisitions import as_descriptor
         if Xq.dim() != 2 or Xq.shape[1] != self.d:
             raise ValueError(f"pool must be (q,{self.d}), got {tuple(Xq.shape)}")
         if not (1 <= k <= _lib.TOPK_MAX):
             raise ValueError(f"k must be in [1,{_lib.TOPK_MAX}]")
+        if precision == "auto":
+            # tensor-core pass + float64 re-score, kept only if the evidence certifies that the selection equals the
+            # float64 mode's (refine_certificate); otherwise the pool is scored again in float64
+            if return_all or k > _lib.REFINE_KMAX:
+                precision = "fp64"
+            else:
+                out = self.score_pool(Xq, acq, k, precision="tf32+refine", index_offset=index_offset,
+                                      running=None if running is None else (running[0].clone(), running[1].clone()),
+                                      host_pool=host_pool)
+                if self.refine_certificate()["certified"]:
+                    self.last_auto_path = "tf32+refine"
+                    if running is not None:
+                        running[0].copy_(out[0])
+                        running[1].copy_(out[1])
+                    return out
+                precision = "fp64"
+            self.last_auto_path = "fp64"
         if precision not in _lib.PRECISIONS:
-            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS) + ['auto']}")
         prec = _lib.PRECISIONS[precision]
         refine = prec == _lib.PREC_TF32_REFINE
         if refine and k > _lib.REFINE_KMAX:

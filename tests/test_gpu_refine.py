@@ -70,7 +70,16 @@ def test_refine_selection_equals_fp64_mode_on_config_shapes(name, func, n, d, q,
     pool = uniform_pool(11, 0, q, d)
     for acq, k in ((B.EI(best), 8), (B.UCB(1.8), 8), (B.PI(best), 3)):
         _, _, cert = _same_selection(gp, pool, acq, k)
-        assert cert["certified"], (name, type(acq).__name__, cert)
+        # config 1 (n=100, d=2, l=0.3: cond(K) ~ 1e8) is the regime where one-pass TF32 is NOT accurate (observed
+        # |TF32 - float64| EI error 0.02 against a k-th score of 0.027): the float64 selection is still reproduced,
+        # and the evidence correctly refuses to certify it -- precision="auto" then falls back to float64
+        if name != "config1":
+            assert cert["certified"], (name, type(acq).__name__, cert)
+    sa, ia = gp.score_pool(pool, B.EI(best), 8, precision="auto")
+    s64, i64 = gp.score_pool(pool, B.EI(best), 8, precision="fp64")
+    assert torch.equal(ia, i64) and torch.allclose(sa, s64, rtol=1e-9, atol=0)
+    if name == "config1":
+        assert gp.last_auto_path == "fp64"
     # float32 candidates: the short-list rows are gathered from the float32 pool
     p32 = pool.float()
     s64, i64 = gp.score_pool(p32, B.EI(best), 8, precision="fp64")
