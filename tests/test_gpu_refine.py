@@ -22,13 +22,18 @@ def _fixed(kind, d, ls, noise=1e-4, iso=False):
                       pairwise_eps=(1e-6 if kind == O.MATERN52 else 0.0))
 
 
-def _same_selection(gp, pool, acq, k):
+def _same_selection(gp, pool, acq, k, must_certify=True):
+    """certified  =>  the float64 selection, with float64-exact scores.  (Uncertified results are allowed to differ:
+    that is what the evidence is for; precision="auto" then re-scores in float64.)"""
     s64, i64 = gp.score_pool(pool, acq, k, precision="fp64")
     sr, ir = gp.score_pool(pool, acq, k, precision="tf32+refine")
     cert = gp.refine_certificate()
-    assert torch.equal(ir, i64), (ir, i64, cert)
-    a, b = np_(sr), np_(s64)
-    assert np.all(np.abs(a - b) <= 1e-9 * np.abs(b) + 1e-300), (a, b)
+    if must_certify:
+        assert cert["certified"], cert
+    if cert["certified"]:
+        assert torch.equal(ir, i64), (ir, i64, cert)
+        a, b = np_(sr), np_(s64)
+        assert np.all(np.abs(a - b) <= 1e-9 * np.abs(b) + 1e-300), (a, b)
     return s64, i64, cert
 
 
@@ -68,18 +73,18 @@ def test_refine_selection_equals_fp64_mode_on_config_shapes(name, func, n, d, q,
     gp = gp_from_params(p, X, y)
     best = float(y.max())
     pool = uniform_pool(11, 0, q, d)
+    # config 1 (n=100, d=2, l=0.3: cond(K) ~ 1e8) is the regime where one-pass TF32 is NOT accurate (observed
+    # |TF32 - float64| score errors of 0.02 (EI) and 0.09 (UCB) against k-th scores of 0.027 / 1.15): the evidence
+    # refuses to certify those selections, and precision="auto" falls back to float64
+    tiny = name == "config1"
     for acq, k in ((B.EI(best), 8), (B.UCB(1.8), 8), (B.PI(best), 3)):
-        _, _, cert = _same_selection(gp, pool, acq, k)
-        # config 1 (n=100, d=2, l=0.3: cond(K) ~ 1e8) is the regime where one-pass TF32 is NOT accurate (observed
-        # |TF32 - float64| EI error 0.02 against a k-th score of 0.027): the float64 selection is still reproduced,
-        # and the evidence correctly refuses to certify it -- precision="auto" then falls back to float64
-        if name != "config1":
-            assert cert["certified"], (name, type(acq).__name__, cert)
-    sa, ia = gp.score_pool(pool, B.EI(best), 8, precision="auto")
-    s64, i64 = gp.score_pool(pool, B.EI(best), 8, precision="fp64")
-    assert torch.equal(ia, i64) and torch.allclose(sa, s64, rtol=1e-9, atol=0)
-    if name == "config1":
-        assert gp.last_auto_path == "fp64"
+        _, _, cert = _same_selection(gp, pool, acq, k, must_certify=not tiny)
+        sa, ia = gp.score_pool(pool, acq, k, precision="auto")
+        s64, i64 = gp.score_pool(pool, acq, k, precision="fp64")
+        assert torch.equal(ia, i64) and torch.allclose(sa, s64, rtol=1e-9, atol=0)
+        assert gp.last_auto_path == ("tf32+refine" if cert["certified"] else "fp64")
+    if tiny:
+        return
     # float32 candidates: the short-list rows are gathered from the float32 pool
     p32 = pool.float()
     s64, i64 = gp.score_pool(p32, B.EI(best), 8, precision="fp64")
@@ -134,4 +139,6 @@ def test_refine_ties_resolve_to_the_lowest_index(cuda_device):
     pool2 = torch.cat([pool[:5000], pool[:5000]])
     s64, i64 = gp.score_pool(pool2, B.UCB(), 8, precision="fp64")
     sr, ir = gp.score_pool(pool2, B.UCB(), 8, precision="tf32+refine")
-    assert torch.equal(ir, i64) and int(i64.max()) < 5000
+    assert torch.equal(ir, i64)
+    lo = np_(i64).reshape(4, 2)          # four best rows, each followed by its copy: lower index first
+    assert np.all(lo[:, 1] == lo[:, 0] + 5000) and np.all(lo[:, 0] < 5000)
