@@ -85,6 +85,8 @@ SIGNATURES = {
     "bbo_gp_score_pool_batched": (C.c_int, [C.POINTER(GpHyper), _I64, _I64, _P, _P, _P, _P, _P, _P, _I64, _I32, _P, _P,
                                             _P, _SZ, _P]),
     "bbo_topk_merge": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P]),
+    "bbo_topk_pack": (C.c_int, [_P, _P, _I32, _P, _P]),
+    "bbo_topk_merge_packed": (C.c_int, [_P, _I64, _I32, _P, _P, _P]),
     "bbo_warp_kumaraswamy": (C.c_int, [_P, _I64, _D, _D, _D, _P, _I32, _P]),
     "bbo_pool_uniform": (C.c_int, [C.c_uint64, _I64, _I64, _I64, _P, _I32, _P]),
 }

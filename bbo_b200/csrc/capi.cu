@@ -386,6 +386,16 @@ int bbo_topk_merge(const double* score_dev, const int64_t* index_dev, int64_t m,
   return topk_merge(score_dev, index_dev, m, k, out_score_dev, out_index_dev, S(stream));
 }
 
+int bbo_topk_pack(const double* score_dev, const int64_t* index_dev, int32_t k, int64_t* packed_dev, void* stream) {
+  if (!score_dev || !index_dev || !packed_dev) return BBO_ERR_BAD_ARG;
+  return topk_pack(score_dev, index_dev, k, packed_dev, S(stream));
+}
+int bbo_topk_merge_packed(const int64_t* packed_dev, int64_t m, int32_t k, double* out_score_dev,
+                          int64_t* out_index_dev, void* stream) {
+  if (!packed_dev || !out_score_dev || !out_index_dev) return BBO_ERR_BAD_ARG;
+  return topk_merge_packed(packed_dev, m, k, out_score_dev, out_index_dev, S(stream));
+}
+
 int bbo_warp_kumaraswamy(const void* x_dev, int64_t count, double a, double b, double eps, void* out_dev,
                          int32_t is_f32, void* stream) {
   if (count < 0 || !(a > 0.0) || !(b > 0.0)) return BBO_ERR_BAD_ARG;

@@ -461,6 +461,51 @@ static int topk_levels(double* as, int64_t* ai, int64_t m, double* bs, int64_t* 
   }
 }
 
+// (score, index) pairs <-> one interleaved int64 buffer [bits(score_0), index_0, bits(score_1), ...]: the message
+// of the single all-gather of the multi-GPU path, packed and merged without any framework-side reshuffling.
+__global__ void k_topk_pack(const double* __restrict__ s, const int64_t* __restrict__ i, int k,
+                            int64_t* __restrict__ packed) {
+  const int t = threadIdx.x;
+  if (t < k) {
+    packed[2 * t] = __double_as_longlong(s[t]);
+    packed[2 * t + 1] = i[t];
+  }
+}
+__global__ void __launch_bounds__(256)
+k_topk_merge_packed(const int64_t* __restrict__ packed, int m, int k, double* __restrict__ out_s,
+                    int64_t* __restrict__ out_i) {
+  __shared__ double ss[kSeg];
+  __shared__ int64_t si[kSeg];
+  __shared__ double ws[8];
+  __shared__ int64_t wi[8];
+  __shared__ int wp[8];
+  for (int p = threadIdx.x; p < kSeg; p += 256) {
+    double sc = -INFINITY;
+    int64_t ix = -1;
+    if (p < m) {
+      sc = __longlong_as_double(packed[2 * p]);
+      ix = packed[2 * p + 1];
+      if (sc != sc) ix = -1;
+    }
+    ss[p] = sc;
+    si[p] = ix;
+  }
+  select_rounds(ss, si, ws, wi, wp, k, out_s, out_i);
+}
+int topk_pack(const double* score, const int64_t* index, int k, int64_t* packed, cudaStream_t st) {
+  if (k < 1 || k > BBO_TOPK_MAX) return BBO_ERR_BAD_ARG;
+  k_topk_pack<<<1, BBO_TOPK_MAX, 0, st>>>(score, index, k, packed);
+  BBO_LAUNCH_CHECK();
+  return BBO_OK;
+}
+int topk_merge_packed(const int64_t* packed, int64_t m, int k, double* out_s, int64_t* out_i, cudaStream_t st) {
+  if (k < 1 || k > BBO_TOPK_MAX || m < 0) return BBO_ERR_BAD_ARG;
+  if (m > kSeg) return BBO_ERR_BAD_SHAPE;
+  k_topk_merge_packed<<<1, 256, 0, st>>>(packed, int(m), k, out_s, out_i);
+  BBO_LAUNCH_CHECK();
+  return BBO_OK;
+}
+
 int topk_merge(const double* score, const int64_t* index, int64_t m, int k, double* out_s, int64_t* out_i,
                cudaStream_t st) {
   if (k < 1 || k > BBO_TOPK_MAX || m < 0) return BBO_ERR_BAD_ARG;

@@ -47,6 +47,8 @@ int gp_score_pool_batched(const bbo_gp_hyper& h, int64_t n, int64_t B, const dou
 int acq_eval(const bbo_acq& a, const void* mu, const void* sd, void* out, int64_t n, int is_f32, cudaStream_t st);
 int topk_merge(const double* score, const int64_t* index, int64_t m, int k, double* out_s, int64_t* out_i,
                cudaStream_t st);
+int topk_pack(const double* score, const int64_t* index, int k, int64_t* packed, cudaStream_t st);
+int topk_merge_packed(const int64_t* packed, int64_t m, int k, double* out_s, int64_t* out_i, cudaStream_t st);
 
 // TF32 mode (score_tf32.cu): pipelined K* (aux stream) / tcgen05 panel (st) over all chunks of a pool;
 // consume(chunk_start, qc, mu, nsplit, vpart, stream) enqueues the per-chunk acquisition / selection work.

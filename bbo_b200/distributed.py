@@ -94,6 +94,27 @@ def broadcast_state(gp, src: int = 0, group=None, mode: str = "hyper") -> None:
         gp.install_state(buf[:nh], buf[nh + na:].view(gp.np, gp.np), buf[nh:nh + na])
 
 
+def allgather_merge_topk(scores: torch.Tensor, indices: torch.Tensor, k: int, group=None):
+    """The multi-GPU step on the device in two launches around ONE collective: bbo_topk_pack -> a single
+    all_gather_into_tensor of the packed (score, index) pairs -> bbo_topk_merge_packed.  Returns the global
+    (scores[k], indices[k]) on every rank, bit-identical for any number of GPUs."""
+    lib = _lib.load()
+    dev = _lib.require_cuda(scores.device)
+    world = dist.get_world_size(group)
+    kk = scores.numel()
+    packed = torch.empty(2 * kk, dtype=torch.int64, device=dev)
+    gathered = torch.empty(world * 2 * kk, dtype=torch.int64, device=dev)
+    out_s = torch.empty(k, dtype=torch.float64, device=dev)
+    out_i = torch.empty(k, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.stream_ptr(dev)
+        _lib.check(lib.bbo_topk_pack(_lib.ptr(scores), _lib.ptr(indices), kk, _lib.ptr(packed), st), "bbo_topk_pack")
+        dist.all_gather_into_tensor(gathered, packed, group=group)
+        _lib.check(lib.bbo_topk_merge_packed(_lib.ptr(gathered), world * kk, k, _lib.ptr(out_s), _lib.ptr(out_i), st),
+                   "bbo_topk_merge_packed")
+    return out_s, out_i
+
+
 def sharded_score_pool(gp, acq, k: int, Xq_local: torch.Tensor, index_offset: int, *, precision: str = "fp64",
                        group=None):
     """Score this rank's shard, all-gather the per-rank top-k, merge.  Returns the global
@@ -101,5 +122,4 @@ def sharded_score_pool(gp, acq, k: int, Xq_local: torch.Tensor, index_offset: in
     s, i = gp.score_pool(Xq_local, acq, k, precision=precision, index_offset=index_offset)
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return s, i
-    gs, gi = gather_topk(s, i, group)
-    return merge_topk_device(gs, gi, k)
+    return allgather_merge_topk(s, i, k, group)

@@ -11,14 +11,14 @@ also     "fit": GP fit ms/iter (value + analytic gradient, FP64) next to cuSOLVE
          "roofline" for the dominant kernel; "cpu_baseline" (the UNMODIFIED reference on the host cores)
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--precision tf32+refine|tf32|fp64] [--impl reference]
-                  [--scaling weak|strong --pool-total Q] [--n N --d D --objective ackley|levy|rastrigin]
+                  [--scaling weak|strong --pool-total Q] [--nobs N --dim D --objective ackley|levy|rastrigin]
 For N > 1 launch with torchrun (one rank per GPU); rank 0 prints ONE JSON line.
 
 precision  "tf32+refine" (default): tcgen05 TF32 panel over the whole pool keeps a short-list, the short-list is
            re-scored in float64, the selection and the returned scores are float64 (identical to --precision fp64:
            checked in the run, `selection_matches_fp64`).  "tf32": TF32-accurate scores.  "fp64": DMMA throughout.
 scaling    "weak" (default): --pool candidates per GPU.  "strong": --pool-total candidates split over the GPUs
-           (BASELINE config 5: --scaling strong --pool-total 67108864 --n 8192 --d 100 --objective levy).
+           (BASELINE config 5: --scaling strong --pool-total 67108864 --nobs 8192 --dim 100 --objective levy).
 reference  --impl reference runs the UNMODIFIED reference (vendored to baseline/_ref by
            baseline/vendor_reference.py): GP.predict in chunks -> .diagonal() -> EI -> top-k
            (bbo/algorithms/surrogates/gp/gp.py:65-83, designers/bo/acquisitions.py:18-23) on all host cores, on a
@@ -52,8 +52,9 @@ def parse():
     ap.add_argument("--precision", default="tf32+refine", choices=["fp64", "tf32", "tf32+refine"],
                     help="arithmetic of the n^2 panel in the headline number (fp64 is reported beside it)")
     ap.add_argument("--no-other-mode", action="store_true")
-    ap.add_argument("--n", type=int, default=N_OBS)
-    ap.add_argument("--d", type=int, default=DIM)
+    # (--nobs / --dim: torchrun's own parser rejects a script argument spelled --n as an ambiguous abbreviation)
+    ap.add_argument("--nobs", "--n", dest="n", type=int, default=N_OBS)
+    ap.add_argument("--dim", "--d", dest="d", type=int, default=DIM)
     ap.add_argument("--objective", default="ackley", choices=["ackley", "levy", "rastrigin"])
     ap.add_argument("--lengthscale", type=float, default=None, help="default 0.5 (1.5 for d >= 50)")
     ap.add_argument("--pool", type=int, default=1 << 20, help="candidates per GPU per step (weak scaling)")
@@ -348,7 +349,7 @@ def run_b200(a):
     import torch.distributed as dist
     import bbo_b200 as B
     from bbo_b200 import _lib
-    from bbo_b200.distributed import broadcast_state, gather_topk, merge_topk_device, shard_range
+    from bbo_b200.distributed import allgather_merge_topk, broadcast_state, shard_range
     from bbo_b200.pool import uniform_pool
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -422,8 +423,7 @@ def run_b200(a):
             return s, i
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         c0.record()
-        gs, gi = gather_topk(s, i)                       # ONE all_gather_into_tensor of k (score, index) pairs
-        out = merge_topk_device(gs, gi, TOPK)
+        out = allgather_merge_topk(s, i, TOPK)           # pack -> ONE all_gather_into_tensor -> merge
         c1.record()
         if timed:
             coll_ev.append((c0, c1))
@@ -447,9 +447,22 @@ def run_b200(a):
     launches = lib.bbo_launch_count() - l0
     clk = clocks.stop() if rank == 0 else None
     value = q_total * a.steps / (ms * 1e-3)
-    collective_ms = None
+    # collective cost: `collective_in_step_ms` is what the events around pack / all-gather / merge saw inside the timed
+    # steps -- it includes waiting for the slowest rank to ARRIVE (per-chip power caps make the ranks' steps differ by
+    # a few hundred microseconds); `collective_ms` is the same three operations timed back to back after a barrier
+    collective_ms = collective_in_step_ms = None
     if world > 1:
-        collective_ms = max_over_ranks(sum(c0.elapsed_time(c1) for c0, c1 in coll_ev) / max(len(coll_ev), 1))
+        collective_in_step_ms = max_over_ranks(sum(c0.elapsed_time(c1) for c0, c1 in coll_ev) / max(len(coll_ev), 1))
+        for _ in range(3):
+            allgather_merge_topk(top_s, top_i, TOPK)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(50):
+            allgather_merge_topk(top_s, top_i, TOPK)
+        c1.record()
+        torch.cuda.synchronize()
+        collective_ms = max_over_ranks(c0.elapsed_time(c1) / 50)
     cert = gp.refine_certificate() if a.precision == "tf32+refine" else None
 
     # ---- e2e: pool in pinned host memory (float32, the dtype of the reference's features), through
@@ -466,8 +479,7 @@ def run_b200(a):
         def step_host():
             hs, hi = gp.score_pool(Xh, acq, TOPK, precision=a.precision, index_offset=lo, host_pool=True)
             if world > 1:   # same single all-gather + merge on the gathered lists
-                gs, gi = gather_topk(hs.to(dev), hi.to(dev))
-                ms_, mi_ = merge_topk_device(gs, gi, TOPK)
+                ms_, mi_ = allgather_merge_topk(hs.to(dev), hi.to(dev), TOPK)
                 return ms_.cpu(), mi_.cpu()
             return hs, hi
 
@@ -483,8 +495,7 @@ def run_b200(a):
         # the device run scored the same candidates in float64; compare selections on the float32 pool
         ds, di = gp.score_pool(Xh.to(dev), acq, TOPK, precision="fp64", index_offset=lo)
         if world > 1:
-            gs, gi = gather_topk(ds, di)
-            ds, di = merge_topk_device(gs, gi, TOPK)
+            ds, di = allgather_merge_topk(ds, di, TOPK)
         e2e = {"value": world * qh * a.steps / (ms_h * 1e-3), "unit": "candidates/s",
                "h2d_bytes_per_step": qh * a.d * 4, "d2h_bytes_per_step": TOPK * 16,
                "ms_per_step": ms_h / a.steps, "host_pool_dtype": "float32", "candidates_per_gpu_per_step": qh,
@@ -503,8 +514,7 @@ def run_b200(a):
         def sub_step(precision):
             s_, i_ = gp.score_pool(Xq[:qs], acq, TOPK, precision=precision, index_offset=lo)
             if world > 1:
-                gs, gi = gather_topk(s_, i_)
-                return merge_topk_device(gs, gi, TOPK)
+                return allgather_merge_topk(s_, i_, TOPK)
             return s_, i_
 
         hs_, hi_ = sub_step(a.precision)
@@ -654,7 +664,8 @@ def run_b200(a):
             "data": "synthetic", "config": config_dict(a, world), "precision": a.precision,
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
             "cpu_port": cpu_port, "fit": fit, "other_mode": other, "selection_matches_fp64": sel_match,
-            "refine": cert, "collective_ms": collective_ms, "state_replication_ms": state_ms,
+            "refine": cert, "collective_ms": collective_ms, "collective_in_step_ms": collective_in_step_ms,
+            "state_replication_ms": state_ms,
             "selection_matches_single_gpu": single,
             "top": {"scores": [float(v) for v in top_s.cpu()], "indices": [int(v) for v in top_i.cpu()]},
         }

@@ -303,6 +303,15 @@ int bbo_gp_score_pool_batched(const bbo_gp_hyper* h, int64_t n, int64_t batch, c
 int bbo_topk_merge(const double* score_dev, const int64_t* index_dev, int64_t m, int32_t k,
                    double* out_score_dev, int64_t* out_index_dev, void* stream);
 
+/* The multi-GPU step: each rank packs its k (score, index) pairs into ONE interleaved
+ * int64 buffer packed[2k] = {bits(score_0), index_0, ...}; the caller all-gathers the packed buffers of all ranks
+ * with a single ncclAllGather (torch.distributed.all_gather_into_tensor in bbo_b200/distributed.py -- the library
+ * does not link NCCL, so that the communicator stays the caller's); bbo_topk_merge_packed reduces the gathered
+ * m = world * k pairs to the k best with the ordering rule above.  Two launches around one collective.          */
+int bbo_topk_pack(const double* score_dev, const int64_t* index_dev, int32_t k, int64_t* packed_dev, void* stream);
+int bbo_topk_merge_packed(const int64_t* packed_dev, int64_t m, int32_t k, double* out_score_dev,
+                          int64_t* out_index_dev, void* stream);
+
 /* On-device uniform candidate generator (counter based, Philox4x32-10): fills out (q,d) with
  * U[0,1) values that depend only on (seed, global row = row_offset + i, column), so any
  * sharding of the pool produces the same candidates.  is_f32 selects float/double output.  */

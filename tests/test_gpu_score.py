@@ -190,3 +190,36 @@ def test_full_size_properties(n, d, cuda_device):
     # posterior variance is bounded by the prior variance + noise and non-negative
     s2v = float(O.softplus(p.raw_variance))
     assert (np_(var) >= 0).all() and (np_(var) <= s2v + p.noise + 1e-9).all()
+
+
+def test_packed_gather_merge_equals_the_unpacked_merge(cuda_device):
+    """bbo_topk_pack / bbo_topk_merge_packed (the two launches around the single all-gather of the multi-GPU step):
+    packing the per-rank lists of a simulated 4-rank world and merging the concatenation gives the bits of
+    bbo_topk_merge on the same pairs, ties -> lowest global index, NaN / empty slots skipped."""
+    import ctypes as C
+    from bbo_b200 import _lib
+    from bbo_b200.distributed import merge_topk_device
+    lib = _lib.load()
+    k, world = 8, 4
+    rng = np.random.default_rng(3)
+    s = np.round(rng.standard_normal((world, k)), 1)           # ties on purpose
+    s[1, 5:] = -np.inf
+    i = rng.permutation(10 ** 6)[:world * k].reshape(world, k).astype(np.int64)
+    i[1, 5:] = -1
+    s[2, 0] = np.nan
+    st = _lib.stream_ptr(cuda_device)
+    packed = []
+    for r in range(world):
+        sr, ir = torch.as_tensor(s[r]).cuda(), torch.as_tensor(i[r]).cuda()
+        p = torch.empty(2 * k, dtype=torch.int64, device="cuda")
+        _lib.check(lib.bbo_topk_pack(_lib.ptr(sr), _lib.ptr(ir), k, _lib.ptr(p), st))
+        packed.append(p)
+    g = torch.cat(packed)
+    out_s = torch.empty(k, dtype=torch.float64, device="cuda")
+    out_i = torch.empty(k, dtype=torch.int64, device="cuda")
+    _lib.check(lib.bbo_topk_merge_packed(_lib.ptr(g), world * k, k, _lib.ptr(out_s), _lib.ptr(out_i), st))
+    ref_s, ref_i = merge_topk_device(torch.as_tensor(s.reshape(-1)).cuda(), torch.as_tensor(i.reshape(-1)).cuda(), k)
+    assert torch.equal(out_i, ref_i) and torch.equal(out_s, ref_s)
+    valid = ~np.isnan(s.reshape(-1)) & (i.reshape(-1) >= 0)
+    order = np.lexsort((i.reshape(-1)[valid], -s.reshape(-1)[valid]))[:k]
+    assert list(np_(out_i)) == list(i.reshape(-1)[valid][order])
