@@ -33,6 +33,7 @@ struct GemmCfg {
 using Cfg128x64 = GemmCfg<128, 64, 32, 32>;  // 8 warps, 64 accumulator registers / thread
 using Cfg64x64 = GemmCfg<64, 64, 32, 32>;    // 4 warps; every block boundary is 64-aligned
 using Cfg64x32 = GemmCfg<64, 32, 32, 16>;    // 4 warps; short-list re-scoring (many small CTAs)
+using Cfg64x64w8 = GemmCfg<64, 64, 16, 32>;  // 8 warps on one 64x64 tile: the single-launch small-problem fit
 
 template <class Cfg>
 struct Acc {

@@ -18,6 +18,27 @@ def _batch(B, n, d, kind, seed):
     return ps, np.stack(Xs), np.stack(ys), theta
 
 
+@pytest.fixture()
+def single_launch():
+    """Force the single-launch small-problem kernel (k_fit_small; default only from 96 problems on)."""
+    import os
+    old = os.environ.get("BBO_FIT_SMALL_MIN_BATCH")
+    os.environ["BBO_FIT_SMALL_MIN_BATCH"] = "1"
+    yield
+    if old is None:
+        del os.environ["BBO_FIT_SMALL_MIN_BATCH"]
+    else:
+        os.environ["BBO_FIT_SMALL_MIN_BATCH"] = old
+
+
+@pytest.mark.parametrize("B,n,d,kind", [(9, 256, 10, O.RBF), (12, 130, 7, O.MATERN52), (8, 500, 33, O.RBF),
+                                        (2, 64, 3, O.MATERN52)])
+def test_single_launch_value_grad_train_and_scoring(B, n, d, kind, cuda_device, single_launch):
+    """The same oracle checks as below with every problem on one CTA of k_fit_small."""
+    test_batched_value_grad_train_and_scoring(B, n, d, kind, cuda_device)
+
+
+# the multi-kernel pipeline with a batch index (the default below 96 problems)
 @pytest.mark.parametrize("B,n,d,kind", [(5, 70, 4, O.MATERN52), (3, 256, 10, O.RBF)])
 def test_batched_value_grad_train_and_scoring(B, n, d, kind, cuda_device):
     import bbo_b200 as B200
@@ -75,3 +96,46 @@ def test_batched_scoring_many_problems_two_groups(cuda_device):
         np.testing.assert_allclose(np_(s[b]), os_, rtol=1e-6, atol=1e-12)
         s1, i1 = gb.problem(b).score_pool(torch.as_tensor(Xq[b]).cuda(), B200.EI(best[b]), k)
         assert torch.equal(i1, i[b]) and torch.equal(s1, s[b])
+
+
+def test_single_launch_fit_equals_the_pipeline(cuda_device):
+    """Config-4 shape: 100 problems of n=256, d=10 (above the default threshold: k_fit_small) against each problem
+    alone through the multi-kernel pipeline (CudaGP, batch = 1): value, gradient, and the Adam trajectory of train()."""
+    import bbo_b200 as B200
+    from bbo_b200.batch import CudaGPBatch
+    from _gpu_helpers import gp_from_params
+    B, n, d = 100, 256, 10
+    ps, X, y, theta = _batch(B, n, d, O.RBF, 4100)
+    gb = CudaGPBatch(torch.as_tensor(X), torch.as_tensor(y)[..., None], "rbf_vmap", theta=torch.as_tensor(theta),
+                     noise_variance=1e-4, epochs=10, lr=0.02)
+    vals, grads = gb.value_and_grad()
+    for b in (0, 7, 99):
+        gp = gp_from_params(ps[b], X[b], y[b], epochs=10, lr=0.02)
+        v, g_ls, g_var, g_c = gp.value_and_grad()                      # raw-parameter gradients
+        sg = O.sigmoid(ps[b].raw_lengthscale).numpy()
+        assert abs(float(vals[b]) - float(v)) <= 1e-10 * abs(float(v))
+        np.testing.assert_allclose(np_(grads[b, :d]) * sg, np_(g_ls), rtol=1e-8, atol=1e-10 * np.abs(np_(g_ls)).max())
+        assert abs(float(grads[b, d + 1]) - float(g_c)) <= 1e-8 * abs(float(g_c)) + 1e-12
+    gb.train()
+    for b in (0, 99):
+        gp = gp_from_params(ps[b], X[b], y[b], epochs=10, lr=0.02)
+        gp.train()
+        np.testing.assert_allclose(np_(gb.last_values[:, b]), np_(gp.last_values), rtol=1e-9)
+        got = np_(gb.theta[b])
+        want = np.concatenate([[float(gp._mean_module.constant)], np_(gp._cov_module.base_kernel.lengthscale),
+                               [float(gp._cov_module.variance)]])
+        np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-12)
+    assert int(gb.info.abs().sum()) == 0
+
+
+def test_single_launch_fit_reports_non_pd(cuda_device, single_launch):
+    """A duplicated observation with zero noise makes one problem's K singular: that problem's info word is set
+    (the leading minor, as torch.linalg.cholesky reports it), the others are untouched."""
+    from bbo_b200.batch import CudaGPBatch
+    B, n, d = 8, 100, 3
+    ps, X, y, theta = _batch(B, n, d, O.RBF, 77)
+    X[3, 40] = X[3, 10]
+    gb = CudaGPBatch(torch.as_tensor(X), torch.as_tensor(y)[..., None], "rbf_vmap", theta=torch.as_tensor(theta),
+                     noise_variance=0.0, epochs=1)
+    with pytest.raises(torch.linalg.LinAlgError):
+        gb.value_and_grad()
