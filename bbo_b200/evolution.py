@@ -27,13 +27,29 @@ import torch
 from .abstractions import GradientFreeOptimizer
 
 
+def tournament_winner(fitness: torch.Tensor, cand: torch.Tensor) -> torch.Tensor:
+    """re1.py:38-45 for R populations at once: fitness (R, P), drawn member indices cand (R, t) -> index of the
+    winner (R,), the FIRST best of the drawn members in draw order (np.argmax semantics; goal MAXIMIZE: the
+    acquisition problem is a maximisation, bo.py:90-92)."""
+    f = fitness.gather(1, cand)
+    best = f.max(dim=1, keepdim=True).values
+    first = (f == best).to(torch.int8).argmax(dim=1, keepdim=True)     # first occurrence of the maximum
+    return cand.gather(1, first).squeeze(1)
+
+
 def tournament_select(fitness: torch.Tensor, tournament_size: int, gen: torch.Generator) -> torch.Tensor:
-    """fitness (R, P) -> winner index (R,): best of `tournament_size` DISTINCT random members."""
+    """fitness (R, P) -> winner index (R,): best of `tournament_size` DISTINCT random members
+    (rng.choice(..., replace=False), re1.py:37)."""
     R, P = fitness.shape
     keys = torch.rand(R, P, generator=gen, device=fitness.device)
     cand = keys.topk(min(tournament_size, P), dim=1).indices           # distinct by construction
-    win = fitness.gather(1, cand).argmax(dim=1, keepdim=True)
-    return cand.gather(1, win).squeeze(1)
+    return tournament_winner(fitness, cand)
+
+
+def apply_mutation(parents: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor) -> torch.Tensor:
+    """re1.py:57-64 for double parameters scaled to [0,1]: coordinates `cols` (R, k) of the parents are replaced by
+    the uniform draws `vals` (R, k) (lb = 0, ub = 1: value = rng.random() * (ub - lb) + lb)."""
+    return parents.scatter(1, cols, vals)
 
 
 def mutate(parents: torch.Tensor, num_mutation: int, gen: torch.Generator) -> torch.Tensor:
@@ -42,7 +58,7 @@ def mutate(parents: torch.Tensor, num_mutation: int, gen: torch.Generator) -> to
     keys = torch.rand(R, d, generator=gen, device=parents.device)
     cols = keys.topk(min(num_mutation, d), dim=1).indices
     vals = torch.rand(R, cols.shape[1], generator=gen, device=parents.device, dtype=parents.dtype)
-    return parents.scatter(1, cols, vals)
+    return apply_mutation(parents, cols, vals)
 
 
 class RingPopulation:
