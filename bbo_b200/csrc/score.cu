@@ -602,14 +602,15 @@ struct RefineScratch {
   int64_t* gi[2];      // (256) indices the rows of Xg[p] belong to
   double* tf_s;        // (256) TF32 scores in the order of the gathered rows
   double* Ks;          // (256, np) float64 cross-covariance of the short-list
-  double* mu;          // (256)
+  double* mu;          // (np/64, 256) partial mean sums, one slot per 64-observation tile
   double* part;        // (np/32, 256) |v|^2 partial sums, one slot per 32-row block of L^-1
   double* la_s;        // (512) selection list: running top-k, then the re-scored short-list
   int64_t* la_i;
 };
 static size_t refine_bytes(int64_t np, int64_t d) {
   const size_t R = kRefineRows;
-  size_t doubles = R + R + 8 + 8 + 2 * R * size_t(d) + 2 * R + R + R * size_t(np) + R + size_t(np / 32) * R + 4 * R;
+  size_t doubles = R + R + 8 + 8 + 2 * R * size_t(d) + 2 * R + R + R * size_t(np) + size_t(np / 64) * R +
+                   size_t(np / 32) * R + 4 * R;
   return doubles * sizeof(double) + 1024;
 }
 static RefineScratch carve_refine(void* base, int64_t np, int64_t d) {
@@ -624,18 +625,20 @@ static RefineScratch carve_refine(void* base, int64_t np, int64_t d) {
   for (int p = 0; p < 2; ++p) { r.gi[p] = reinterpret_cast<int64_t*>(q);  q += R; }
   r.tf_s = q;  q += R;
   r.Ks = q;  q += R * size_t(np);
-  r.mu = q;  q += R;
+  r.mu = q;  q += size_t(np / 64) * R;
   r.part = q;  q += size_t(np / 32) * R;
   r.la_s = q;  q += 2 * R;
   r.la_i = reinterpret_cast<int64_t*>(q);  q += 2 * R;
   return r;
 }
 
-__global__ void k_refine_init(double* sh_s, int64_t* sh_i, double* bound, int m) {
+__global__ void k_refine_init(double* sh_s, int64_t* sh_i, double* bound, int64_t* gi0, int64_t* gi1, int m) {
   const int t = threadIdx.x;
   if (t < m) {
     sh_s[t] = -INFINITY;
     sh_i[t] = -1;
+    gi0[t] = -1;      // row-buffer indices: slots past the short-list length must never match a carried index
+    gi1[t] = -1;
   }
   if (t == 0) *bound = -INFINITY;
 }
@@ -662,35 +665,66 @@ k_refine_bound(const double* __restrict__ seg_s, const int64_t* __restrict__ seg
 
 // Rows of the short-listed candidates -> Xg_new (float64), in short-list order.  A candidate of this call's pool
 // [lo, lo+q) is read from Xq; one carried over from an earlier (continued) call is found by index in the previous
-// row buffer.  One block, 256 threads.
+// row buffer.  One block of 256 threads, one warp per row; rows [0, rows) are written (rows = m rounded up to 64).
 template <typename T1>
 __global__ void __launch_bounds__(256)
 k_refine_gather(const T1* __restrict__ Xq, int64_t lo, int64_t q, int d, const double* __restrict__ sh_s,
-                const int64_t* __restrict__ sh_i, int m, const double* __restrict__ Xg_prev,
+                const int64_t* __restrict__ sh_i, int m, int rows, const double* __restrict__ Xg_prev,
                 const int64_t* __restrict__ gi_prev, double* __restrict__ Xg_new, int64_t* __restrict__ gi_new,
                 double* __restrict__ tf_s) {
-  __shared__ int src;
-  for (int j = 0; j < kRefineRows; ++j) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = warp; j < rows; j += 8) {
     const int64_t ix = j < m ? sh_i[j] : -1;
     const bool local = ix >= lo && ix < lo + q;
-    if (threadIdx.x == 0) src = -1;
-    __syncthreads();
-    if (ix >= 0 && !local && gi_prev != nullptr && gi_prev[threadIdx.x] == ix) src = threadIdx.x;
-    __syncthreads();
-    const int sp = src;
-    int64_t keep = ix;
-    for (int c = threadIdx.x; c < d; c += 256) {
+    int sp = -1;
+    if (ix >= 0 && !local && gi_prev != nullptr) {
+      for (int u = 0; u < kRefineRows / 32 && sp < 0; ++u) {
+        const unsigned hit = __ballot_sync(0xffffffffu, gi_prev[lane + 32 * u] == ix);
+        if (hit) sp = 32 * u + __ffs(int(hit)) - 1;
+      }
+    }
+    for (int c = lane; c < d; c += 32) {
       double v = 0.0;
       if (ix >= 0 && local) v = static_cast<double>(Xq[(ix - lo) * d + c]);
       else if (ix >= 0 && sp >= 0) v = Xg_prev[int64_t(sp) * d + c];
       Xg_new[int64_t(j) * d + c] = v;
     }
-    if (ix >= 0 && !local && sp < 0) keep = -1;   // cannot happen (every carried index is in gi_prev); drop it if so
-    if (threadIdx.x == 0) {
-      gi_new[j] = keep;
+    if (lane == 0) {
+      // (every carried index is in gi_prev; if it were not, the row is dropped rather than scored as zeros)
+      gi_new[j] = (ix >= 0 && !local && sp < 0) ? -1 : ix;
       tf_s[j] = j < m ? sh_s[j] : -INFINITY;
     }
-    __syncthreads();
+  }
+}
+
+// Float64 cross-covariance of the short-list against ONE 64-observation tile per CTA (k_kstar walks all tiles in one
+// CTA: fine for a pool, 0.69 ms for a 64-row short-list at n = 4096).  Ks (rows, np) and, per observation tile, the
+// partial mean sums mupart[jt, c] = sum_{j in tile jt} Ks[c,j] alpha[j], added in tile order by k_refine_acq.
+// grid (np/64, rows/64), 256 threads.
+__global__ void __launch_bounds__(256)
+k_refine_kstar(bbo_gp_hyper h, const double* __restrict__ Xg, int64_t rows, const double* __restrict__ X, int64_t n,
+               int64_t np, const double* __restrict__ hyp, const double* __restrict__ alpha,
+               double* __restrict__ Ks, double* __restrict__ mupart) {
+  __shared__ double x1s[64 * kXS], x2s[64 * kXS], ils[kDC];
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int64_t j0 = int64_t(blockIdx.x) * 64, c0 = int64_t(blockIdx.y) * 64;
+  const double eps = h.kind == BBO_KERNEL_MATERN52 ? h.pairwise_eps : 0.0;
+  const double s2 = hyp[2 * h.d];
+  double s[4][4];
+  dist_tile_q<double>(Xg, rows, c0, X, n, j0, h.d, hyp + h.d, eps, s, x1s, x2s, ils);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    double macc = 0.0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int64_t j = j0 + tx + 16 * b;
+      const double v = (j < n) ? s2 * kernel_from_s(h.kind, s[a][b]) : 0.0;
+      Ks[(c0 + ty * 4 + a) * np + j] = v;
+      macc = fma(v, alpha[j], macc);
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) macc += __shfl_xor_sync(0xffffffffu, macc, o);
+    if (tx == 0) mupart[int64_t(blockIdx.x) * kRefineRows + c0 + ty * 4 + a] = macc;
   }
 }
 
@@ -732,7 +766,7 @@ k_refine_vnorm(const double* __restrict__ Ks, const double* __restrict__ Linv, i
 
 // float64 acquisition of the re-scored short-list + the selection list [running top-k | short-list] + evidence.
 __global__ void __launch_bounds__(kRefineRows)
-k_refine_acq(bbo_gp_hyper h, bbo_acq a, const double* __restrict__ hyp, const double* __restrict__ mu,
+k_refine_acq(bbo_gp_hyper h, bbo_acq a, const double* __restrict__ hyp, const double* __restrict__ mupart, int nmu,
              const double* __restrict__ part, int nblk, const int64_t* __restrict__ gi,
              const double* __restrict__ tf_s, int m, int k, int keep_running, const double* __restrict__ run_s,
              const int64_t* __restrict__ run_i, double* __restrict__ la_s, int64_t* __restrict__ la_i,
@@ -748,7 +782,10 @@ k_refine_acq(bbo_gp_hyper h, bbo_acq a, const double* __restrict__ hyp, const do
     double vn = 0.0;
     for (int b = 0; b < nblk; ++b) vn += part[int64_t(b) * kRefineRows + c];
     const double var = kxx - vn + h.noise;
-    double sc = acq_value<double>(a, mu[c], sqrt(var));
+    double mu = 0.0;
+    for (int b = 0; b < nmu; ++b) mu += mupart[int64_t(b) * kRefineRows + c];
+    mu += hyp[2 * h.d + 1];
+    double sc = acq_value<double>(a, mu, sqrt(var));
     int64_t ix = gi[c];
     if (ix >= 0 && sc != sc) {
       ix = -1;
@@ -872,8 +909,8 @@ static int refine_rescore(const bbo_gp_state& s, const bbo_acq& acq, const Score
   const int64_t np = w.np;
   const int rows = int(ceil_div(m, 64) * 64);
   prof_begin(kProfKstar, st);
-  k_kstar<double><<<unsigned(rows / 64), 256, 0, st>>>(s.h, r.Xg[par], rows, s.X, s.n, np, s.hyp, s.alpha, r.Ks, r.mu,
-                                                      kRefineRows);
+  k_refine_kstar<<<dim3(unsigned(np / 64), unsigned(rows / 64)), 256, 0, st>>>(s.h, r.Xg[par], rows, s.X, s.n, np,
+                                                                              s.hyp, s.alpha, r.Ks, r.mu);
   BBO_LAUNCH_CHECK();
   prof_end(kProfKstar, st);
   prof_begin(kProfVnorm, st);
@@ -882,7 +919,7 @@ static int refine_rescore(const bbo_gp_state& s, const bbo_acq& acq, const Score
   BBO_LAUNCH_CHECK();
   prof_end(kProfVnorm, st);
   prof_begin(kProfSelect, st);
-  k_refine_acq<<<1, kRefineRows, 0, st>>>(s.h, acq, s.hyp, r.mu, r.part, int(np / 32), r.gi[par], r.tf_s, m, k,
+  k_refine_acq<<<1, kRefineRows, 0, st>>>(s.h, acq, s.hyp, r.mu, int(np / 64), r.part, int(np / 32), r.gi[par], r.tf_s, m, k,
                                           keep_running ? 1 : 0, topk_s, topk_i, r.la_s, r.la_i, r.info, nan_count);
   BBO_LAUNCH_CHECK();
   k_topk_seg<<<1, 256, 0, st>>>(r.la_s, r.la_i, 0, int64_t(k) + m, k, topk_s, topk_i);
@@ -926,7 +963,7 @@ int gp_score_pool(const bbo_gp_state& s, const bbo_acq& acq, int precision, cons
   if (refine) {
     r = carve_refine(w.refine, w.np, s.h.d);
     if (!(refine_flags & kRefineContinue)) {
-      k_refine_init<<<1, kRefineRows, 0, st>>>(r.sh_s, r.sh_i, r.bound, kRefineRows);
+      k_refine_init<<<1, kRefineRows, 0, st>>>(r.sh_s, r.sh_i, r.bound, r.gi[0], r.gi[1], kRefineRows);
       BBO_LAUNCH_CHECK();
     }
   } else if (!keep_running) {
@@ -993,13 +1030,14 @@ int gp_score_pool(const bbo_gp_state& s, const bbo_acq& acq, int precision, cons
     // rows of the short-list -> the row buffer of this call's parity (the other one holds the previous call's)
     const int par = (refine_flags & kRefineParity) ? 1 : 0;
     const bool cont = (refine_flags & kRefineContinue) != 0;
+    const int grows = int(ceil_div(m, 64) * 64);
     if (xq_is_f32)
       k_refine_gather<float><<<1, 256, 0, st>>>(static_cast<const float*>(Xq), index_offset, q, s.h.d, r.sh_s, r.sh_i,
-                                                m, cont ? r.Xg[par ^ 1] : nullptr, cont ? r.gi[par ^ 1] : nullptr,
-                                                r.Xg[par], r.gi[par], r.tf_s);
+                                                m, grows, cont ? r.Xg[par ^ 1] : nullptr,
+                                                cont ? r.gi[par ^ 1] : nullptr, r.Xg[par], r.gi[par], r.tf_s);
     else
       k_refine_gather<double><<<1, 256, 0, st>>>(static_cast<const double*>(Xq), index_offset, q, s.h.d, r.sh_s,
-                                                 r.sh_i, m, cont ? r.Xg[par ^ 1] : nullptr,
+                                                 r.sh_i, m, grows, cont ? r.Xg[par ^ 1] : nullptr,
                                                  cont ? r.gi[par ^ 1] : nullptr, r.Xg[par], r.gi[par], r.tf_s);
     BBO_LAUNCH_CHECK();
     if (refine_flags & kRefineDefer) return BBO_OK;
