@@ -431,6 +431,170 @@ k_topk_merge_running(const double* __restrict__ as, const int64_t* __restrict__ 
   select_rounds(ss, si, ws, wi, wp, k, run_s, run_i);
 }
 
+// ------------------------------------------------------------------------------------------
+// Threshold-filtered selection (default).  After the first chunks of a pool almost no candidate can enter the
+// running list any more, yet the round-based kernels above pay k (or, for the tf32+refine short-list, 2k + 64)
+// block-wide arg-max rounds per chunk (51 + 59 us per chunk in round 2's launch list).  Here a candidate is compared
+// with the CURRENT last entry of the running list (read at kernel start: stream-ordered behind the previous chunk's
+// merge) and only candidates that beat it are appended, through a counter, to a survivor buffer; a block in which
+// more than 64 candidates pass (first chunks, or a pool sorted by score) falls back to the arg-max rounds locally
+// and appends its own K best.  k_merge_survivors then merges the few survivors into the running list by RANKING
+// (every pair compared once, ~1 us) or, for many survivors, by arg-max rounds in batches.
+// The result is the same set as before: the K best by (score desc, index asc) of a set does not depend on the
+// order in which its members arrive, so atomics may order the survivor buffer freely.
+// ------------------------------------------------------------------------------------------
+constexpr int kFilterLocal = 64;   // more passing candidates than this in one block -> local arg-max rounds
+
+__global__ void __launch_bounds__(256)
+k_acq_filter(bbo_gp_hyper h, bbo_acq a, int clamp_var, const double* __restrict__ hyp,
+             const double* __restrict__ mu, const double* __restrict__ vpart, int nsplit, int64_t qc_pad, int64_t qc,
+             int64_t base, int K, const double* __restrict__ run_s, const int64_t* __restrict__ run_i,
+             double* __restrict__ mu_out, double* __restrict__ var_out, double* __restrict__ score_out,
+             int32_t* __restrict__ nan_count, double* __restrict__ surv_s, int64_t* __restrict__ surv_i,
+             int* __restrict__ surv_count) {
+  __shared__ double ss[kSeg];
+  __shared__ int64_t si[kSeg];
+  __shared__ double ws[8];
+  __shared__ int64_t wi[8];
+  __shared__ int wp[8];
+  __shared__ int s_base;
+  const int tid = threadIdx.x;
+  const int64_t s0 = int64_t(blockIdx.x) * kSeg;
+  const double eps = h.kind == BBO_KERNEL_MATERN52 ? h.pairwise_eps : 0.0;
+  const double kxx = hyp[2 * h.d] * kernel_from_s(h.kind, double(h.d) * eps * eps);
+  const double thr_s = run_s[K - 1];
+  const int64_t thr_i = run_i[K - 1];
+  double sc[kSeg / 256];
+  int64_t ix[kSeg / 256];
+  int nans = 0, npass = 0;
+#pragma unroll
+  for (int u = 0; u < kSeg / 256; ++u) {
+    const int64_t c = s0 + tid + 256 * u;
+    sc[u] = -INFINITY;
+    ix[u] = -1;
+    if (c < qc) {
+      const double vn = sum_vpart(vpart, nsplit, qc_pad, c);
+      double var = kxx - vn + h.noise;
+      if (clamp_var) var = fmax(var, 0.0);
+      const double m = mu[c];
+      const double v = acq_value<double>(a, m, sqrt(var));
+      if (mu_out) mu_out[c] = m;
+      if (var_out) var_out[c] = var;
+      if (score_out) score_out[c] = v;
+      if (v != v) ++nans;
+      else if (better(v, base + c, thr_s, thr_i)) {
+        sc[u] = v;
+        ix[u] = base + c;
+        ++npass;
+      }
+    }
+  }
+  if (nans && nan_count) atomicAdd(nan_count, nans);
+  const int total = __syncthreads_count(npass > 0) == 0 ? 0 : -1;
+  if (total == 0) return;                       // nothing in this segment beats the running list
+  // block-wide number of passing candidates
+  int cnt = npass;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((tid & 31) == 0) wp[tid >> 5] = cnt;
+  __syncthreads();
+  int block_pass = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) block_pass += wp[w];
+  __syncthreads();
+  if (block_pass <= kFilterLocal) {
+#pragma unroll
+    for (int u = 0; u < kSeg / 256; ++u)
+      if (ix[u] >= 0) {
+        const int p = atomicAdd(surv_count, 1);
+        surv_s[p] = sc[u];
+        surv_i[p] = ix[u];
+      }
+    return;
+  }
+  // many candidates pass: this block's own K best (arg-max rounds over the staged segment)
+#pragma unroll
+  for (int u = 0; u < kSeg / 256; ++u) {
+    ss[tid + 256 * u] = sc[u];
+    si[tid + 256 * u] = ix[u];
+  }
+  const int kk = block_pass < K ? block_pass : K;
+  if (tid == 0) s_base = atomicAdd(surv_count, kk);
+  __syncthreads();
+  select_rounds(ss, si, ws, wi, wp, kk, surv_s + s_base, surv_i + s_base);
+}
+
+// Merge the survivors of one chunk into the running list (K entries, sorted) and reset the counter.  One block.
+__global__ void __launch_bounds__(256)
+k_merge_survivors(const double* __restrict__ surv_s, const int64_t* __restrict__ surv_i, int* __restrict__ surv_count,
+                  int K, double* __restrict__ run_s, int64_t* __restrict__ run_i) {
+  __shared__ double ss[kSeg];
+  __shared__ int64_t si[kSeg];
+  __shared__ double ws[8];
+  __shared__ int64_t wi[8];
+  __shared__ int wp[8];
+  const int tid = threadIdx.x;
+  const int c = *surv_count;
+  __syncthreads();
+  if (tid == 0) *surv_count = 0;
+  if (c == 0) return;
+  if (K + c <= 512) {
+    // ranking merge: position of an element = number of elements that beat it (keys are distinct: indices are)
+    const int nu = K + c;
+    for (int p = tid; p < nu; p += 256) {
+      ss[p] = p < K ? run_s[p] : surv_s[p - K];
+      si[p] = p < K ? run_i[p] : surv_i[p - K];
+    }
+    __syncthreads();
+    int rank[2] = {-1, -1};
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int e = tid + 256 * u;
+      if (e < nu && si[e] >= 0) {
+        const double es = ss[e];
+        const int64_t ei = si[e];
+        int r = 0;
+        for (int x = 0; x < nu; ++x) r += better(ss[x], si[x], es, ei) ? 1 : 0;
+        rank[u] = r;
+      }
+    }
+    __syncthreads();
+    for (int p = tid; p < K; p += 256) {       // fewer than K valid entries leave (-inf, -1) behind them
+      run_s[p] = -INFINITY;
+      run_i[p] = -1;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int e = tid + 256 * u;
+      if (rank[u] >= 0 && rank[u] < K) {
+        run_s[rank[u]] = ss[e];
+        run_i[rank[u]] = si[e];
+      }
+    }
+    return;
+  }
+  // many survivors (first chunks): arg-max rounds over [running list | batch of survivors], batch after batch
+  for (int b0 = 0; b0 < c; b0 += kSeg - K) {
+    const int nb = (c - b0 < kSeg - K) ? c - b0 : kSeg - K;
+    for (int p = tid; p < kSeg; p += 256) {
+      double sc = -INFINITY;
+      int64_t ix = -1;
+      if (p < K) {
+        sc = run_s[p];
+        ix = run_i[p];
+      } else if (p < K + nb) {
+        sc = surv_s[b0 + p - K];
+        ix = surv_i[b0 + p - K];
+      }
+      ss[p] = sc;
+      si[p] = ix;
+    }
+    select_rounds(ss, si, ws, wi, wp, K, run_s, run_i);
+    __syncthreads();
+  }
+}
+
 __global__ void k_topk_init(double* s, int64_t* i, int k) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < k) {
@@ -538,7 +702,7 @@ size_t ScoreWorkspace::bytes(int64_t n, int64_t d, int64_t q_chunk, int precisio
   const size_t ks = (tf32 && !want_full) ? 0 : size_t(qp) * np;   // TF32 keeps K* in float32
   size_t doubles = ks * (want_full ? 2 : 1)  // Ks (+V)
                    + size_t(kMaxSplit) * qp + 2 * size_t(qp)  // vpart, mu, score
-                   + 2 * (size_t(BBO_TOPK_MAX) * (nblk + 1) + 256) * 2;  // two (score,index) ping-pong lists
+                   + 2 * (size_t(256) * (nblk + 1) + 256) * 2 + 32;  // two (score,index) lists + survivor counter
   size_t extra = 0;
   if (tf32) extra = score_tf32_extra_bytes(n, d, qp);
   if (precision == BBO_PREC_TF32_REFINE) extra += refine_bytes(np, d);
@@ -564,7 +728,7 @@ int ScoreWorkspace::bind(void* ws, size_t ws_bytes, int64_t n, int64_t d, int64_
   score = q;
   q += qp;
   const int64_t nblk = ceil_div(qp, kSeg);
-  list_len = int64_t(BBO_TOPK_MAX) * (nblk + 1) + 256;
+  list_len = int64_t(256) * (nblk + 1) + 256;
   la_s = q;
   q += list_len;
   lb_s = q;
@@ -573,6 +737,8 @@ int ScoreWorkspace::bind(void* ws, size_t ws_bytes, int64_t n, int64_t d, int64_
   q += list_len;
   lb_i = reinterpret_cast<int64_t*>(q);
   q += list_len;
+  surv_count = reinterpret_cast<int*>(q);
+  q += 32;
   tf32 = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(q) + 255) & ~uintptr_t(255));
   refine = nullptr;
   if (precision == BBO_PREC_TF32_REFINE)
@@ -958,6 +1124,7 @@ int gp_score_pool(const bbo_gp_state& s, const bbo_acq& acq, int precision, cons
   ScoreWorkspace w;
   rc = w.bind(ws, ws_bytes, s.n, s.h.d, q_chunk, precision, false);
   if (rc != BBO_OK) return rc;
+  BBO_CUDA_CHECK(cudaMemsetAsync(w.surv_count, 0, sizeof(int), st));
   RefineScratch r{};
   const int m = refine ? refine_shortlist_len(k) : 0, kseg = refine ? refine_kseg(k) : 0;
   if (refine) {
@@ -976,8 +1143,24 @@ int gp_score_pool(const bbo_gp_state& s, const bbo_acq& acq, int precision, cons
     prof_begin(kProfSelect, sc);
     const int64_t nb = ceil_div(qc, kSeg);
     static const bool unfused = getenv("BBO_SELECT_UNFUSED") != nullptr;
-    if (refine) {
-      // TF32 scores -> per-segment lists of kseg = 2k entries -> running short-list of m entries (by TF32 score)
+    static const bool rounds_only = getenv("BBO_SELECT_ROUNDS") != nullptr;   // round-based selection everywhere
+    // running list of this mode: the k best (score, index) pairs, or the tf32+refine short-list (m entries)
+    const int K = refine ? m : k;
+    double* run_s = refine ? r.sh_s : topk_s;
+    int64_t* run_i = refine ? r.sh_i : topk_i;
+    if (!unfused && !rounds_only && nb * int64_t(K > kFilterLocal ? K : kFilterLocal) <= w.list_len) {
+      // threshold filter (default): only candidates that beat the current last entry of the running list survive
+      k_acq_filter<<<unsigned(nb), 256, 0, sc>>>(
+          s.h, acq, tf32, s.hyp, mu_chunk, vpart, nsplit, w.qp, qc, index_offset + c0, K, run_s, run_i,
+          mu_out ? mu_out + c0 : nullptr, var_out ? var_out + c0 : nullptr, score_out ? score_out + c0 : nullptr,
+          nan_count, w.la_s, w.la_i, w.surv_count);
+      BBO_LAUNCH_CHECK();
+      k_merge_survivors<<<1, 256, 0, sc>>>(w.la_s, w.la_i, w.surv_count, K, run_s, run_i);
+      BBO_LAUNCH_CHECK();
+    } else if (refine) {
+      // round-based fallback (BBO_SELECT_ROUNDS=1 or a chunk too large for the survivor buffer): TF32 scores ->
+      // per-segment lists of kseg = 2k entries -> running short-list of m entries (by TF32 score); what a segment
+      // dropped is bounded by its kseg-th entry (k_refine_bound)
       if (nb * kseg + m > w.list_len) return BBO_ERR_WORKSPACE;
       k_acq_topk<<<unsigned(nb), 256, 0, sc>>>(
           s.h, acq, 1, s.hyp, mu_chunk, vpart, nsplit, w.qp, qc, index_offset + c0, kseg,

@@ -18,6 +18,7 @@ struct ScoreWorkspace {
   int64_t list_len = 0;
   double *la_s = nullptr, *lb_s = nullptr;   // top-k ping-pong lists
   int64_t *la_i = nullptr, *lb_i = nullptr;
+  int* surv_count = nullptr;   // survivor counter of the threshold-filtered selection
   void* tf32 = nullptr;        // TF32-mode scratch (score_tf32.cu)
   void* refine = nullptr;      // BBO_PREC_TF32_REFINE scratch (short-list, gathered rows, small FP64 buffers)
 
