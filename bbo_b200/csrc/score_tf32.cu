@@ -6,7 +6,8 @@
 //   K* producers (cross-covariance of a chunk, TF32-rounded float32, fused with mu = c + K* alpha)
 //     k_kstar_umma       d <= 30      tcgen05 kind::tf32, one 3xTF32 contraction over concatenated hi/lo rows,
 //                                     TMA operand loads, TMEM accumulator ring, TMA tensor stores
-//     k_kstar_mma2       30 < d <= 126  mma.sync 3xTF32 with the two augmentation columns
+//     k_kstar_umma_stream 30 < d <= 126 the same contraction with BOTH operands streamed in 32-word boxes
+//     k_kstar_mma2       (mma.sync 3xTF32 with the two augmentation columns; A/B reference for the two above)
 //     k_kstar_f32_fast   126 < d <= 192 CUDA cores, expanded form;   k_kstar_f32  any d, exact-difference form
 //   n^2 panel (V = L^-1 k* is never written: the epilogue squares and row-sums the accumulators)
 //     k_vnorm_tf32_2sm<true>   persistent CTA pairs walking a work list (k_panel_schedule): default while the
@@ -1177,14 +1178,20 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 namespace ku {
 constexpr int BM = 128, BN = 128, BOXK = 32;
 constexpr int BOX_BYTES = 128 * BOXK * 4;          // 16 KB: 128 rows x 128 bytes
-constexpr int MAXBOX = 3;                          // 3 dk <= 96, dk <= 32
+constexpr int MAXBOX = 3;                          // resident-A form: 3 dk <= 96, dk <= 32
+constexpr int MAXBOX_STREAM = 12;                  // streaming form: 3 dk <= 384, dk <= 128
+constexpr int SSTAGES = 4;                         // streaming form: ring of (A box + B box) stages
 constexpr int BSTAGES = 2, ACCS = 4;
 constexpr int EPI_WARPS = 16;
 constexpr int THREADS = 64 + 32 * EPI_WARPS;       // 576
 constexpr int OUT_BYTES = 32 * 128;                // staging tile: 32 candidates x 32 values
-constexpr int kMaxD = 30;
+constexpr int kMaxD = 30;                          // resident-A form
+constexpr int kMaxDStream = 126;                   // streaming form (dk = 8 ceil((d+2)/8) <= 128)
 static size_t smem_bytes(int nbox) {
   return size_t(nbox) * BOX_BYTES * (1 + BSTAGES) + size_t(EPI_WARPS) * OUT_BYTES + 1024;
+}
+static size_t smem_bytes_stream() {
+  return size_t(SSTAGES) * 2 * BOX_BYTES + size_t(EPI_WARPS) * OUT_BYTES + 1024;
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t saddr, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -1468,6 +1475,207 @@ k_kstar_umma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   }
 }
 
+// Streaming form of k_kstar_umma for 30 < d <= 126 (BASELINE configs 3 and 5: d = 50, 100): with 3 dk up to 384
+// words the candidate tile (up to 192 KB) no longer fits beside the observation ring, so BOTH operands are streamed
+// in 32-word boxes through a ring of ku::SSTAGES (A box + B box) stages; accumulator ring, epilogue and TMA store are
+// those of k_kstar_umma.  L2 -> SM traffic: 2 x nbox x 16 KB per 128 x 128 block.
+template <bool MATERN>
+__global__ void __launch_bounds__(ku::THREADS, 1)
+k_kstar_umma_stream(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+             const __grid_constant__ CUtensorMap mapO, int np, int tiles, int nbox, int ksteps, int d,
+             const double* __restrict__ hyp, const float* __restrict__ alpha32, double* __restrict__ mu) {
+  using namespace tf;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_full[ku::SSTAGES], s_empty[ku::SSTAGES], t_full[ku::ACCS], t_empty[ku::ACCS];
+  __shared__ uint32_t tmem_base_sh;
+  __shared__ float mu_sh[2][3][ku::BM];
+  __shared__ __align__(16) float al_sh[ku::EPI_WARPS][2][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  constexpr int stage_bytes = 2 * ku::BOX_BYTES;   // one ring stage: a 128 x 32-word box of each operand
+  const int nblk = np / ku::BN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ku::SSTAGES; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 1);
+    }
+    for (int a = 0; a < ku::ACCS; ++a) {
+      mbar_init(&t_full[a], 1);
+      mbar_init(&t_empty[a], ku::EPI_WARPS * 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_sh;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ===== TMA producer =====
+      uint32_t phase = 0;
+      int stage = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int nb = 0; nb < nblk; ++nb) {
+          for (int b = 0; b < nbox; ++b) {           // box b of BOTH operands: the candidate tile does not stay resident
+            mbar_wait(&s_empty[stage], phase ^ 1);
+            uint8_t* sa = sgen + stage * stage_bytes;
+            mbar_expect_tx(&s_full[stage], uint32_t(stage_bytes));
+            tma_load_2d(sa, &mapA, &s_full[stage], b * ku::BOXK, tile * ku::BM);
+            tma_load_2d(sa + ku::BOX_BYTES, &mapB, &s_full[stage], b * ku::BOXK, nb * ku::BN);
+            if (++stage == ku::SSTAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {   // ===== MMA issuer =====
+      // D=f32, A=B=tf32, both K-major, N=128, M=128
+      const uint32_t idesc =
+          (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(ku::BN >> 3) << 17) | (uint32_t(ku::BM >> 4) << 24);
+      uint32_t phase = 0, acc_phase = 0;
+      int stage = 0, acc = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int nb = 0; nb < nblk; ++nb) {
+          mbar_wait(&t_empty[acc], acc_phase ^ 1);
+          const uint32_t d_tmem = tmem_base + uint32_t(acc * ku::BN);
+          for (int b = 0; b < nbox; ++b) {
+            mbar_wait(&s_full[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = sbase + uint32_t(stage * stage_bytes);
+            const int nks = ksteps - 4 * b < 4 ? ksteps - 4 * b : 4;     // K = 8 steps inside this 32-word box
+            for (int ks = 0; ks < nks; ++ks) {
+              const uint64_t adv = uint64_t(ks * 2);   // 32 bytes inside the 128-byte swizzle atom
+              tc_mma_tf32(d_tmem, make_desc(sa) + adv, make_desc(sa + ku::BOX_BYTES) + adv, idesc,
+                          (b | ks) != 0 ? 1u : 0u);
+            }
+            tc_commit(&s_empty[stage]);
+            if (++stage == ku::SSTAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          tc_commit(&t_full[acc]);
+          if (++acc == ku::ACCS) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
+        }
+      }
+    }
+  } else {   // ===== epilogue (warps 2..17) =====
+    // warp = (TMEM lane quarter, 32-column slab): 16 warps, four per scheduler, so that one warp's TMEM load, MUFU
+    // and TMA-store latencies are covered by the other three
+    const int ew = warp - 2, quarter = warp & 3, colq = ew >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t stg = sbase + uint32_t(ku::SSTAGES * stage_bytes + ew * ku::OUT_BYTES);
+    const float s2 = float(hyp[2 * d]);
+    const float l2s2 = __log2f(s2);
+    const float kLog2e = 1.4426950408889634f;
+    const double cmean = hyp[2 * d + 1];
+    const uint32_t tlane = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(colq * 32);
+    const float* abase = alpha32 + colq * 32;
+    float m = 0.f;
+    // alpha of this warp's 32 columns, one block ahead (cp.async, per-warp double buffer): the values are used
+    // once per tile, so they always come from L2
+    float* alw = &al_sh[ew][0][0];
+    auto alpha_fetch = [&](int nb_, int buf_) {
+      if (lane < 8) {
+        const unsigned sa = smem_u32(alw + buf_ * 32 + lane * 4);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(abase + nb_ * ku::BN + lane * 4)
+                     : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int my_tiles = (tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+    const int nblocks = my_tiles * nblk;     // 128 x 128 blocks this CTA produces, accumulators in ring order
+    uint32_t acc_phase = 0;
+    int acc = 0;
+    if (nblocks > 0) alpha_fetch(0, 0);
+    int tile = blockIdx.x, nb = 0, tcount = 0;
+    for (int blk = 0; blk < nblocks; ++blk) {
+      const int nb_next = (nb + 1 == nblk) ? 0 : nb + 1;
+      const float* al = alw + (blk & 1) * 32;
+      alpha_fetch(nb_next, (blk + 1) & 1);                       // next block's alpha (harmless after the last)
+      uint32_t r[32];
+      mbar_wait(&t_full[acc], acc_phase);
+      tc_fence_after();
+      tmem_ld32_issue(tlane + uint32_t(acc * ku::BN), r);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");      // this block's alpha has landed
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile is free again
+      __syncwarp();
+      tmem_ld_wait(r);
+      tc_fence_before();
+      mbar_arrive(&t_empty[acc]);
+      if (++acc == ku::ACCS) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+      // values -> K*, mu partial, TF32 bits into the swizzled staging tile, TMA store
+      const uint32_t sdst = stg + uint32_t(lane * 128);
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        uint32_t u[4];
+        const float4 av = *reinterpret_cast<const float4*>(al + c4 * 4);
+        const float a4[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float x = __uint_as_float(r[c4 * 4 + e]);
+          float val;
+          if (!MATERN) {
+            val = ex2_approx(fminf(x, l2s2));
+          } else {
+            const float rr = 2.2360679775f * sqrtf(fmaxf(x, 0.f));
+            val = s2 * fmaf(rr, fmaf(rr, 1.f / 3.f, 1.f), 1.f) * ex2_approx(-kLog2e * rr);
+          }
+          m = fmaf(val, a4[e], m);
+          u[e] = round_tf32_bits(val);
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdst + uint32_t((c4 ^ (lane & 7)) * 16)),
+                     "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3])
+                     : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();                          // staging tile complete; all lanes are done with al
+      if (lane == 0) {
+        ku::tma_store_2d(&mapO, stg, nb * ku::BN + colq * 32, tile * ku::BM + quarter * 32);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      if (nb_next == 0) {
+        // mu = c + the four column slabs in a fixed order
+        if (colq > 0) mu_sh[tcount & 1][colq - 1][row] = m;
+        asm volatile("bar.sync 1, %0;" ::"n"(ku::EPI_WARPS * 32) : "memory");
+        if (colq == 0)
+          mu[int64_t(tile) * ku::BM + row] =
+              cmean + double(((m + mu_sh[tcount & 1][0][row]) + mu_sh[tcount & 1][1][row]) + mu_sh[tcount & 1][2][row]);
+        m = 0.f;
+        tile += gridDim.x;
+        ++tcount;
+      }
+      nb = nb_next;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 template <int KS>
 static size_t kstar_mma2_smem() {
   constexpr int DK = KS * 8, LS = 4 * ((DK / 4 + 1) | 1);
@@ -1535,8 +1743,8 @@ size_t score_tf32_extra_bytes(int64_t n, int64_t d, int64_t qp) {
          align256(size_t(np) * d * sizeof(float)) + 2 * align256(size_t(np) * sizeof(float)) +
          2 * align256(size_t(np) * (d + 16) * sizeof(uint32_t)) +
          align256(size_t(qp) * 2 * (d + 16) * sizeof(uint32_t)) +
-         align256(size_t(qp) * 32 * ku::MAXBOX * sizeof(uint32_t)) +
-         align256(size_t(np) * 32 * ku::MAXBOX * sizeof(uint32_t)) + 2 * align256(size_t(32) * qp * sizeof(double)) + 256;
+         align256(size_t(qp) * 32 * ku::MAXBOX_STREAM * sizeof(uint32_t)) +
+         align256(size_t(np) * 32 * ku::MAXBOX_STREAM * sizeof(uint32_t)) + 2 * align256(size_t(32) * qp * sizeof(double)) + 256;
 }
 
 static Tf32Scratch carve(const ScoreWorkspace& w, int64_t d) {
@@ -1565,9 +1773,9 @@ static Tf32Scratch carve(const ScoreWorkspace& w, int64_t d) {
   t.Bfrag = reinterpret_cast<uint32_t*>(p);
   p += align256(size_t(w.qp) * 2 * (d + 16) * sizeof(uint32_t));
   t.Aop = reinterpret_cast<uint32_t*>(p);
-  p += align256(size_t(w.qp) * 32 * ku::MAXBOX * sizeof(uint32_t));
+  p += align256(size_t(w.qp) * 32 * ku::MAXBOX_STREAM * sizeof(uint32_t));
   t.Bop = reinterpret_cast<uint32_t*>(p);
-  p += align256(size_t(w.np) * 32 * ku::MAXBOX * sizeof(uint32_t));
+  p += align256(size_t(w.np) * 32 * ku::MAXBOX_STREAM * sizeof(uint32_t));
   for (int i = 0; i < 2; ++i) {
     t.vp32[i] = reinterpret_cast<double*>(p);
     p += align256(size_t(32) * w.qp * sizeof(double));
@@ -1656,7 +1864,9 @@ static int get_aux(Tf32Aux** out) {
 // default for 30 < d <= 126) -- used by the test that checks both producers give the same selection.
 static bool use_kstar_umma(int d) {
   static const bool off = getenv("BBO_KSTAR_NO_UMMA") != nullptr;
-  return !off && d <= ku::kMaxD;
+  // 30 < d <= 126: the streaming tcgen05 form (round 2); BBO_KSTAR_NO_UMMA_STREAM=1 keeps k_kstar_mma2 there
+  static const bool no_stream = getenv("BBO_KSTAR_NO_UMMA_STREAM") != nullptr;
+  return !off && (d <= ku::kMaxD || (!no_stream && d <= ku::kMaxDStream));
 }
 static int sm_count() {
   static int sms[64] = {};
@@ -1697,14 +1907,31 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
     if (rc != BBO_OK) return rc;
     const int tiles = int(qc_pad / ku::BM);
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    const size_t sm = ku::smem_bytes(nbox);
     const double* hyp = s.hyp;
-    if (matern)
-      k_kstar_umma<true><<<unsigned(grid), ku::THREADS, sm, st>>>(mapA, mapB, mapO, int(np), tiles, nbox, 3 * dk / 8,
-                                                                 s.h.d, hyp, t.alpha32, mu_chunk);
-    else
-      k_kstar_umma<false><<<unsigned(grid), ku::THREADS, sm, st>>>(mapA, mapB, mapO, int(np), tiles, nbox, 3 * dk / 8,
-                                                                  s.h.d, hyp, t.alpha32, mu_chunk);
+    if (nbox > ku::MAXBOX) {   // streaming form: both operands in boxes through one ring
+      static DeviceOnce stream_attr_once;
+      if (stream_attr_once.first()) {
+        BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_umma_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            int(ku::smem_bytes_stream())));
+        BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_umma_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            int(ku::smem_bytes_stream())));
+      }
+      const size_t sm = ku::smem_bytes_stream();
+      if (matern)
+        k_kstar_umma_stream<true><<<unsigned(grid), ku::THREADS, sm, st>>>(mapA, mapB, mapO, int(np), tiles, nbox,
+                                                                          3 * dk / 8, s.h.d, hyp, t.alpha32, mu_chunk);
+      else
+        k_kstar_umma_stream<false><<<unsigned(grid), ku::THREADS, sm, st>>>(mapA, mapB, mapO, int(np), tiles, nbox,
+                                                                           3 * dk / 8, s.h.d, hyp, t.alpha32, mu_chunk);
+    } else {
+      const size_t sm = ku::smem_bytes(nbox);
+      if (matern)
+        k_kstar_umma<true><<<unsigned(grid), ku::THREADS, sm, st>>>(mapA, mapB, mapO, int(np), tiles, nbox, 3 * dk / 8,
+                                                                   s.h.d, hyp, t.alpha32, mu_chunk);
+      else
+        k_kstar_umma<false><<<unsigned(grid), ku::THREADS, sm, st>>>(mapA, mapB, mapO, int(np), tiles, nbox, 3 * dk / 8,
+                                                                    s.h.d, hyp, t.alpha32, mu_chunk);
+    }
   } else if (s.h.d <= kMma2MaxD) {
     const int ks = (s.h.d + 2 + 7) / 8;
     const unsigned grid = unsigned(qc_pad / 128);

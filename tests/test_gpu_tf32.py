@@ -19,8 +19,10 @@ TOL = 1e-3
     (100, 20, 700, O.RBF),          # np = 128: a single, zero-padded 256-row block
     (300, 20, 5000, O.MATERN52),    # np = 384: partial last block
     (1024, 20, 20000, O.RBF),       # config-2 shape, > 148 tiles (chunk of 148 x 128)
-    (515, 33, 3000, O.MATERN52),    # d not a multiple of 4
-    (260, 100, 2000, O.RBF),        # config-5 dimensionality
+    (515, 33, 3000, O.MATERN52),    # d not a multiple of 4; streaming tcgen05 K* producer, 4 boxes
+    (260, 100, 2000, O.RBF),        # config-5 dimensionality: 10 boxes (3 dk = 312)
+    (700, 50, 30000, O.MATERN52),   # config-3 dimensionality, persistent CTAs with > 1 tile each, 6 boxes
+    (300, 126, 1500, O.RBF),        # largest d of the streaming producer: 12 full boxes
     (2100, 20, 3000, O.RBF),        # np >= 2048: nine 256-row blocks, persistent panel work list
     (2060, 18, 1500, O.MATERN52),   # same, Matern
     (200, 4, 1000, O.RBF),          # tcgen05 K* producer: one 32-word operand box (3 dk = 24)
