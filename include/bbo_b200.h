@@ -32,8 +32,10 @@
  *     memory owned by the caller; "host" pointers are host memory.  All data buffers and
  *     workspaces are the caller's.  The library itself keeps, per device and created on
  *     first use, only scheduling aids: auxiliary streams and events (fit pipeline, TF32
- *     scoring pipeline, host-pool copies) and 128 KB of device memory for the cached work
- *     lists of the persistent TF32 panel.  One host thread per device.
+ *     scoring pipeline, host-pool copies), cached CUDA graphs of the fit iteration and 256 KB of
+ *     device memory for the cached work lists of the persistent TF32 panel.  These caches are
+ *     guarded by mutexes, so calls from several host threads are safe; calls that target the SAME
+ *     device serialise where they share a cache (host-pool scoring, the cached fit graph).
  *   - all matrices row-major, contiguous; float64 unless stated.
  *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it
  *     unless the description says they synchronise.
