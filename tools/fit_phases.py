@@ -78,4 +78,4 @@ al = torch.cholesky_solve(yd[:, None], Lc)[:, 0]
 ref = float(-0.5 * (yd * al).sum() - torch.log(torch.diagonal(Lc)).sum() - 0.5 * n * np.log(2 * np.pi))
 print(json.dumps({"n": n, "d": d, "ms_per_iter": total, "train_ms_per_epoch": train_ms, "epochs": E, "phases_ms": ph, "value": float(v), "torch_value": ref,
                   "rel_err": abs(float(v) - ref) / abs(ref), "grad_c": float(g_c),
-                  "chol_v1": os.environ.get("BBO_FIT_CHOL_V1") is not None}))
+                  }))
