@@ -490,8 +490,7 @@ k_acq_filter(bbo_gp_hyper h, bbo_acq a, int clamp_var, const double* __restrict_
     }
   }
   if (nans && nan_count) atomicAdd(nan_count, nans);
-  const int total = __syncthreads_count(npass > 0) == 0 ? 0 : -1;
-  if (total == 0) return;                       // nothing in this segment beats the running list
+  if (__syncthreads_count(npass > 0) == 0) return;   // nothing in this segment beats the running list (the usual case)
   // block-wide number of passing candidates
   int cnt = npass;
 #pragma unroll
@@ -501,7 +500,7 @@ k_acq_filter(bbo_gp_hyper h, bbo_acq a, int clamp_var, const double* __restrict_
   int block_pass = 0;
 #pragma unroll
   for (int w = 0; w < 8; ++w) block_pass += wp[w];
-  __syncthreads();
+  __syncthreads();                              // wp is reused by select_rounds below
   if (block_pass <= kFilterLocal) {
 #pragma unroll
     for (int u = 0; u < kSeg / 256; ++u)
