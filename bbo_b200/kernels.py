@@ -78,79 +78,97 @@ class ConstantMean(nn.Module):
 # modules evaluated on the GPU -- the O(n^3) objective / O(n^2 q) posterior they feed is the CUDA
 # library (``bbo_b200.warped.CudaWarpedGP``).
 # ---------------------------------------------------------------------------------------------
-class MLPBlock(nn.Module):
-    """warpers.py:8-28: Linear -> [norm] -> activation -> [dropout]."""
-
-    def __init__(self, in_d: int, out_d: int, norm=nn.BatchNorm1d, activation=nn.ReLU, dropout: float = 0.1,
-                 bias: bool = True):
-        super().__init__()
-        mlp = [nn.Linear(in_d, out_d, bias)]
-        if norm is not None:
-            mlp.append(norm(out_d))
-        mlp.append(activation())
-        if dropout > 0:
-            mlp.append(nn.Dropout(dropout))
-        self.mlp = nn.Sequential(*mlp)
-
-    def forward(self, X: torch.Tensor) -> torch.Tensor:
-        return self.mlp(X)
+def _reference_modules():
+    """The reference's own warp / learned-mean / WarpKernel modules when `bbo` is importable (they are plain torch
+    modules whose arithmetic this package does not replace), else None."""
+    try:
+        from bbo.algorithms.surrogates.gp.kernels import WarpKernel as _WK  # type: ignore
+        from bbo.algorithms.surrogates.gp.means import MLPMean as _MM  # type: ignore
+        from bbo.algorithms.surrogates.gp.warpers import KumarWarp as _KW, MLPBlock as _MB, MLPWarp as _MW  # type: ignore
+        return _MB, _MW, _KW, _MM, _WK
+    except Exception:  # noqa: BLE001 - reference absent: the structurally identical fallbacks below are used
+        return None
 
 
-class MLPWarp(nn.Module):
-    """warpers.py:31-49."""
+_REF = _reference_modules()
+if _REF is not None:
+    MLPBlock, MLPWarp, KumarWarp, MLPMean, WarpKernel = _REF
+else:
+    # Fallbacks for environments without the reference: same constructor signatures, attribute names and forward
+    # arithmetic as warpers.py:8-65, means.py:28-35, kernels.py:59-68, so that state dicts interchange.
+    class MLPBlock(nn.Module):
+        """warpers.py:8-28: Linear -> [norm] -> activation -> [dropout]."""
 
-    def __init__(self, in_d: int, hidden_d, norm=None, activation=nn.Tanh, dropout: float = 0.0,
-                 bias: bool = True):
-        super().__init__()
-        layers = []
-        for h in hidden_d:
-            layers.append(MLPBlock(in_d, h, norm, activation, dropout, bias))
-            in_d = h
-        self.layers = nn.Sequential(*layers)
+        def __init__(self, in_d: int, out_d: int, norm=nn.BatchNorm1d, activation=nn.ReLU, dropout: float = 0.1,
+                     bias: bool = True):
+            super().__init__()
+            mlp = [nn.Linear(in_d, out_d, bias)]
+            if norm is not None:
+                mlp.append(norm(out_d))
+            mlp.append(activation())
+            if dropout > 0:
+                mlp.append(nn.Dropout(dropout))
+            self.mlp = nn.Sequential(*mlp)
 
-    def forward(self, X: torch.Tensor) -> torch.Tensor:
-        return self.layers(X)
-
-
-class KumarWarp(nn.Module):
-    """warpers.py:52-65: Kumaraswamy CDF 1 - (1 - x^a)^b on inputs clipped to [1e-6, 1 - 1e-6],
-    a = softplus(alpha), b = softplus(beta)."""
-
-    def __init__(self):
-        super().__init__()
-        self.alpha = nn.Parameter(torch.zeros(1))
-        self.beta = nn.Parameter(torch.zeros(1))
-        self.eps = 1e-6
-
-    def forward(self, X: torch.Tensor) -> torch.Tensor:
-        X = X.clip(self.eps, 1 - self.eps)
-        a = torch.nn.functional.softplus(self.alpha)
-        b = torch.nn.functional.softplus(self.beta)
-        return 1 - (1 - X.pow(a)).pow(b)
+        def forward(self, X: torch.Tensor) -> torch.Tensor:
+            return self.mlp(X)
 
 
-class MLPMean(nn.Module):
-    """means.py:28-35: mean(X) = Linear(in_d, 1)(warp_module(X))."""
+    class MLPWarp(nn.Module):
+        """warpers.py:31-49."""
 
-    def __init__(self, in_d: int, warp_module: nn.Module):
-        super().__init__()
-        self.warp_module = warp_module
-        self.mean = nn.Linear(in_d, 1)
+        def __init__(self, in_d: int, hidden_d, norm=None, activation=nn.Tanh, dropout: float = 0.0,
+                     bias: bool = True):
+            super().__init__()
+            layers = []
+            for h in hidden_d:
+                layers.append(MLPBlock(in_d, h, norm, activation, dropout, bias))
+                in_d = h
+            self.layers = nn.Sequential(*layers)
 
-    def forward(self, X: torch.Tensor) -> torch.Tensor:
-        return self.mean(self.warp_module(X))
+        def forward(self, X: torch.Tensor) -> torch.Tensor:
+            return self.layers(X)
 
 
-class WarpKernel(nn.Module):
-    """kernels.py:59-68: K(X1, X2) = base_kernel(warp(X1), warp(X2))."""
+    class KumarWarp(nn.Module):
+        """warpers.py:52-65: Kumaraswamy CDF 1 - (1 - x^a)^b on inputs clipped to [1e-6, 1 - 1e-6],
+        a = softplus(alpha), b = softplus(beta)."""
 
-    def __init__(self, base_kernel: nn.Module, warp_module: nn.Module):
-        super().__init__()
-        self.warp_module = warp_module
-        self.base_kernel = base_kernel
+        def __init__(self):
+            super().__init__()
+            self.alpha = nn.Parameter(torch.zeros(1))
+            self.beta = nn.Parameter(torch.zeros(1))
+            self.eps = 1e-6
 
-    def forward(self, X1: torch.Tensor, X2: torch.Tensor) -> torch.Tensor:
-        return self.base_kernel(self.warp_module(X1), self.warp_module(X2))
+        def forward(self, X: torch.Tensor) -> torch.Tensor:
+            X = X.clip(self.eps, 1 - self.eps)
+            a = torch.nn.functional.softplus(self.alpha)
+            b = torch.nn.functional.softplus(self.beta)
+            return 1 - (1 - X.pow(a)).pow(b)
+
+
+    class MLPMean(nn.Module):
+        """means.py:28-35: mean(X) = Linear(in_d, 1)(warp_module(X))."""
+
+        def __init__(self, in_d: int, warp_module: nn.Module):
+            super().__init__()
+            self.warp_module = warp_module
+            self.mean = nn.Linear(in_d, 1)
+
+        def forward(self, X: torch.Tensor) -> torch.Tensor:
+            return self.mean(self.warp_module(X))
+
+
+    class WarpKernel(nn.Module):
+        """kernels.py:59-68: K(X1, X2) = base_kernel(warp(X1), warp(X2))."""
+
+        def __init__(self, base_kernel: nn.Module, warp_module: nn.Module):
+            super().__init__()
+            self.warp_module = warp_module
+            self.base_kernel = base_kernel
+
+        def forward(self, X1: torch.Tensor, X2: torch.Tensor) -> torch.Tensor:
+            return self.base_kernel(self.warp_module(X1), self.warp_module(X2))
 
 
 def split_warps(cov_module: nn.Module):
