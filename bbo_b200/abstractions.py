@@ -50,6 +50,11 @@ except Exception:  # noqa: BLE001 - the reference may be absent or its optional 
 try:  # the designers package imports gpytorch, which is usually missing
     from bbo.algorithms.designers.bo.acquisitions import AcquisitionFunction  # type: ignore
 except Exception:  # noqa: BLE001
+    # a failed package import leaves its already-imported children in sys.modules; a later, successful import of
+    # bbo.algorithms.designers (e.g. once gpytorch or its stub is available) would then trip over them
+    for _k in [k for k in sys.modules if k.startswith("bbo.algorithms.designers")]:
+        sys.modules.pop(_k, None)
+
     class AcquisitionFunction(abc.ABC):
         @abc.abstractmethod
         def __call__(self, mu, stddev):
