@@ -20,6 +20,7 @@
 //   Triangular: row block nb only contracts k < (nb+1)*256.
 // SASS evidence: UTCHMMA(.2CTA) / UTMALDG / UTMASTG / LDTM / SYNCS (see profiles/).
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <mutex>
 #include <vector>
 
@@ -113,6 +114,15 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // K-major operand tile, rows of 128 bytes, 128-byte swizzle (what TMA SWIZZLE_128B writes):
 // start address >> 4, LBO = 1 (unused for swizzled K-major), SBO = 1024 B (8 rows), version 1, layout 2
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
@@ -178,9 +188,9 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
 // k < 256(b+1).  Accumulation slots as in k_vnorm_tf32 (bit-identical results).
 // ------------------------------------------------------------------------------------------
 namespace tfp {
-constexpr int BM = 128, BN = 256, BK = 16, UK = 8, STAGES = 5;
-constexpr int A_BYTES = BM * BK * 4;      // 8 KB
-constexpr int B_BYTES = BN * BK * 4;      // 16 KB
+constexpr int BM = 128, BN = 256, BK = 32, UK = 16, STAGES = 5;   // BK binary16 values = 64-byte rows
+constexpr int A_BYTES = BM * BK * 2;      // 8 KB
+constexpr int B_BYTES = BN * BK * 2;      // 16 KB
 constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
 // K-major tile, rows of 64 bytes, 64-byte swizzle: SBO = 512 B (8 rows), layout type 4
@@ -195,6 +205,13 @@ __device__ __forceinline__ uint64_t make_desc64(uint32_t saddr) {
 }
 }  // namespace tfp
 
+// The panel contracts correlations (K* / sigma^2, in (0, 1]) with 2^e L^-1 (k_make_f16): its sums of squares are
+// 2^2e / sigma^4 times |L^-1 k*|^2.  lscale[0] = 2^-2e (a power of two: the product below is exact in float64).
+__device__ __forceinline__ double panel_factor(const double* __restrict__ hyp, int d, const float* __restrict__ lscale) {
+  const double s2 = hyp[2 * d];
+  return s2 * s2 * double(__ldg(lscale));
+}
+
 // CL = 2: clusters of two CTAs (adjacent candidate tiles, same row blocks).  Each CTA loads HALF of
 // every L^-1 tile and TMA-multicasts it to both, so the B operand crosses L2->SM once per cluster;
 // a stage is released to the producers only when BOTH tensor cores have consumed it
@@ -202,7 +219,8 @@ __device__ __forceinline__ uint64_t make_desc64(uint32_t saddr) {
 template <int CL>
 __global__ void __launch_bounds__(tf::THREADS, 1)
 k_vnorm_tf32_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int np,
-                  int64_t qc_pad, double* __restrict__ vpart) {
+                  int64_t qc_pad, double* __restrict__ vpart, const double* __restrict__ hyp, int d,
+                  const float* __restrict__ lscale) {
   using namespace tf;
   uint32_t cta_rank = 0;
   if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
@@ -280,8 +298,8 @@ k_vnorm_tf32_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     }
   } else if (warp == 1) {
     if (lane == 0) {   // ===== MMA issuer =====
-      const uint32_t idesc =
-          (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(tfp::BN >> 3) << 17) | (uint32_t(tfp::BM >> 4) << 24);
+      // D = f32, A = B = f16 (format 0), both K-major
+      const uint32_t idesc = (1u << 4) | (uint32_t(tfp::BN >> 3) << 17) | (uint32_t(tfp::BM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int b0 = blockIdx.y; b0 < nblk; b0 += 2 * S) {
@@ -302,13 +320,13 @@ k_vnorm_tf32_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             const uint64_t bdesc = tfp::make_desc64(sa + tfp::A_BYTES);
 #pragma unroll
             for (int kk = 0; kk < tfp::BK / tfp::UK; ++kk)
-              tc_mma_tf32(tmem_base, adesc + uint64_t(kk * 2), bdesc + uint64_t(kk * 2), idesc, (k | kk) != 0 ? 1u : 0u);
+              tc_mma_f16(tmem_base, adesc + uint64_t(kk * 2), bdesc + uint64_t(kk * 2), idesc, (k | kk) != 0 ? 1u : 0u);
           }
           if (has1) {
             const uint64_t bdesc = tfp::make_desc64(sa + tfp::A_BYTES + tfp::B_BYTES);
 #pragma unroll
             for (int kk = 0; kk < tfp::BK / tfp::UK; ++kk)
-              tc_mma_tf32(tmem_base + uint32_t(tfp::BN), adesc + uint64_t(kk * 2), bdesc + uint64_t(kk * 2), idesc,
+              tc_mma_f16(tmem_base + uint32_t(tfp::BN), adesc + uint64_t(kk * 2), bdesc + uint64_t(kk * 2), idesc,
                           (k | kk) != 0 ? 1u : 0u);
           }
           if (CL == 1) tc_commit(&empty_bar[stage]);
@@ -327,6 +345,7 @@ k_vnorm_tf32_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     double tot0 = 0.0, tot1 = 0.0, tot2 = 0.0, tot3 = 0.0;
+    const double fac = panel_factor(hyp, d, lscale);
     uint32_t acc_phase = 0;
     for (int b0 = blockIdx.y; b0 < nblk; b0 += 2 * S) {
 #pragma unroll
@@ -352,10 +371,11 @@ k_vnorm_tf32_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           part += (s0 + s1) + (s2 + s3);
         }
         const int slot = nb & 3;
-        if (slot == 0) tot0 += double(part);
-        else if (slot == 1) tot1 += double(part);
-        else if (slot == 2) tot2 += double(part);
-        else tot3 += double(part);
+        const double dp = double(part) * fac;
+        if (slot == 0) tot0 += dp;
+        else if (slot == 1) tot1 += dp;
+        else if (slot == 2) tot2 += dp;
+        else tot3 += dp;
         tc_fence_before();
         mbar_arrive(&tempty_bar[a]);
       }
@@ -393,9 +413,9 @@ k_vnorm_tf32_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 // Row-block pairing, triangular bounds and accumulation slots are those of k_vnorm_tf32_pair.
 // ------------------------------------------------------------------------------------------
 namespace tf2 {
-constexpr int BM = 128, BN = 256, BK = 16, UK = 8, STAGES = 8;
-constexpr int A_BYTES = BM * BK * 4;            // 8 KB
-constexpr int BH_BYTES = (BN / 2) * BK * 4;     // 8 KB: this CTA's half of one L^-1 tile
+constexpr int BM = 128, BN = 256, BK = 32, UK = 16, STAGES = 8;   // BK binary16 values = 64-byte rows
+constexpr int A_BYTES = BM * BK * 2;            // 8 KB
+constexpr int BH_BYTES = (BN / 2) * BK * 2;     // 8 KB: this CTA's half of one L^-1 tile
 constexpr int STAGE_BYTES = A_BYTES + 2 * BH_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
@@ -418,12 +438,12 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* ma
       ::"r"(tf::smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void mma_tf32_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void mma_f16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -437,7 +457,8 @@ __device__ __forceinline__ void commit_2sm(uint64_t* bar) {
 template <bool PERSIST>
 __global__ void __launch_bounds__(tf::THREADS, 1)
 k_vnorm_tf32_2sm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int np,
-                 int64_t qc_pad, double* __restrict__ vpart, int shrink, const int* __restrict__ sched, int maxj) {
+                 int64_t qc_pad, double* __restrict__ vpart, int shrink, const int* __restrict__ sched, int maxj,
+                 const double* __restrict__ hyp, int d, const float* __restrict__ lscale) {
   using namespace tf;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[tf2::STAGES], empty_bar[tf2::STAGES], tfull_bar[2], tempty_bar[2];
@@ -530,10 +551,10 @@ k_vnorm_tf32_2sm(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
   } else if (warp == 1) {
     if (lane == 0 && leader) {   // ===== MMA issuer (leader CTA only) =====
-      // D=f32, A=B=tf32, K-major, N=256, M=256 (two SMs).  In the diagonal 256 x 256 block of a row block the rows
-      // above the stage's first column are zero and sit at the end of the block (k_make_tf32): N shrinks by 16
+      // D=f32, A=B=f16, K-major, N=256, M=256 (two SMs).  In the diagonal 256 x 256 block of a row block the rows
+      // above the stage's first column are zero and sit at the end of the block (k_make_tf32): N shrinks by 32
       // per stage there, so the diagonal blocks cost 17/32 of a full block instead of 1 (BBO_TF32_FULL_DIAG=1: off)
-      const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(256 >> 4) << 24);
+      const uint32_t idesc_base = (1u << 4) | (uint32_t(256 >> 4) << 24);   // D = f32, A = B = f16 (format 0)
       const uint32_t idesc = idesc_base | (uint32_t(tf2::BN >> 3) << 17);
       auto idesc_for = [&](int k, int b) -> uint32_t {
         const int kk = k - b * tf2::BN;              // columns into the diagonal block (multiple of 16), < 0 above it
@@ -562,7 +583,7 @@ k_vnorm_tf32_2sm(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             const uint32_t id0 = idesc_for(k, b0);
 #pragma unroll
             for (int kk = 0; kk < tf2::BK / tf2::UK; ++kk)
-              tf2::mma_tf32_2sm(tmem_base, adesc + uint64_t(kk * 2), bdesc + uint64_t(kk * 2), id0,
+              tf2::mma_f16_2sm(tmem_base, adesc + uint64_t(kk * 2), bdesc + uint64_t(kk * 2), id0,
                                 (k | kk) != 0 ? 1u : 0u);
           }
           if (has1) {
@@ -570,7 +591,7 @@ k_vnorm_tf32_2sm(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             const uint32_t id1 = idesc_for(k, b1);
 #pragma unroll
             for (int kk = 0; kk < tf2::BK / tf2::UK; ++kk)
-              tf2::mma_tf32_2sm(tmem_base + uint32_t(tf2::BN), adesc + uint64_t(kk * 2), bdesc + uint64_t(kk * 2),
+              tf2::mma_f16_2sm(tmem_base + uint32_t(tf2::BN), adesc + uint64_t(kk * 2), bdesc + uint64_t(kk * 2),
                                 id1, (k | kk) != 0 ? 1u : 0u);
           }
           tf2::commit_2sm(&empty_bar[stage]);                        // frees the stage in both CTAs
@@ -591,6 +612,7 @@ k_vnorm_tf32_2sm(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     double tot0 = 0.0, tot1 = 0.0, tot2 = 0.0, tot3 = 0.0;
+    const double fac = panel_factor(hyp, d, lscale);
     uint32_t acc_ph[2] = {0, 0};
     for (int j = 0;; ++j) {
       int b0, b1, c0;
@@ -619,13 +641,14 @@ k_vnorm_tf32_2sm(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           part += (s0 + s1) + (s2 + s3);
         }
         if (PERSIST) {   // one slot per row block; k_acq / k_acq_topk add them with the four-slot association
-          vpart[int64_t(nb) * qc_pad + c0 + row] = double(part);
+          vpart[int64_t(nb) * qc_pad + c0 + row] = double(part) * fac;
         } else {
           const int slot = nb & 3;
-          if (slot == 0) tot0 += double(part);
-          else if (slot == 1) tot1 += double(part);
-          else if (slot == 2) tot2 += double(part);
-          else tot3 += double(part);
+          const double dp = double(part) * fac;
+          if (slot == 0) tot0 += dp;
+          else if (slot == 1) tot1 += dp;
+          else if (slot == 2) tot2 += dp;
+          else tot3 += dp;
         }
         tc_fence_before();
         tf2::mbar_arrive_cluster(tf2::map_to_cta(smem_u32(&tempty_bar[a]), 0));   // leader's barrier
@@ -714,7 +737,7 @@ constexpr int kFC = 32, kFS = kFC + 1;
 template <typename T1>
 __global__ void __launch_bounds__(256)
 k_kstar_f32(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const double* __restrict__ X, int64_t n,
-            int64_t np, const double* __restrict__ hyp, const double* __restrict__ alpha, float* __restrict__ Ks,
+            int64_t np, const double* __restrict__ hyp, const double* __restrict__ alpha, __half* __restrict__ Ks,
             double* __restrict__ mu) {
   __shared__ float x1s[64 * kFS], x2s[64 * kFS], ils[kFC];
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
@@ -770,15 +793,13 @@ k_kstar_f32(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const double*
         if (j < n) {
           if (matern) {
             float r = 2.2360679775f * sqrtf(s[a][b]);
-            v = s2 * (1.f + r + r * r * (1.f / 3.f)) * __expf(-r);
+            v = (1.f + r + r * r * (1.f / 3.f)) * __expf(-r);
           } else {
-            v = s2 * __expf(-0.5f * s[a][b]);
+            v = __expf(-0.5f * s[a][b]);
           }
         }
         macc[a] = fmaf(v, float(alpha[j]), macc[a]);
-        uint32_t u;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-        Ks[(c0 + ty * 4 + a) * np + j] = __uint_as_float(u);
+        Ks[(c0 + ty * 4 + a) * np + j] = __float2half_rn(v);      // correlation; sigma^2 enters mu and the panel factor
       }
   }
 #pragma unroll
@@ -786,7 +807,7 @@ k_kstar_f32(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const double*
     float v = macc[a];
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (tx == 0) mu[c0 + ty * 4 + a] = hyp[2 * d + 1] + double(v);
+    if (tx == 0) mu[c0 + ty * 4 + a] = hyp[2 * d + 1] + double(s2) * double(v);
   }
 }
 
@@ -829,7 +850,7 @@ template <typename T1>
 __global__ void __launch_bounds__(256)
 k_kstar_f32_fast(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const float* __restrict__ Xs,
                  const float* __restrict__ bnorm, int64_t n, int64_t np, const double* __restrict__ hyp,
-                 const float* __restrict__ alpha32, float* __restrict__ Ks, double* __restrict__ mu) {
+                 const float* __restrict__ alpha32, __half* __restrict__ Ks, double* __restrict__ mu) {
   extern __shared__ __align__(16) float ksm[];
   const int d = h.d;
   const int d4 = (d + 3) >> 2;
@@ -919,15 +940,13 @@ k_kstar_f32_fast(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const fl
           const float sq = fmaxf(fmaf(-2.f, acc[a][b], an[a] + bn), 0.f);
           if (matern) {
             const float r = 2.2360679775f * sqrtf(sq);
-            v = s2 * (1.f + r + r * r * (1.f / 3.f)) * __expf(-r);
+            v = (1.f + r + r * r * (1.f / 3.f)) * __expf(-r);
           } else {
-            v = s2 * __expf(-0.5f * sq);
+            v = __expf(-0.5f * sq);
           }
         }
         macc[a] = fmaf(v, al, macc[a]);
-        uint32_t u;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-        Ks[(c0 + ty + 16 * a) * np + j] = __uint_as_float(u);
+        Ks[(c0 + ty + 16 * a) * np + j] = __float2half_rn(v);
       }
     }
     __syncthreads();
@@ -937,7 +956,7 @@ k_kstar_f32_fast(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const fl
     float v = macc[a];
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (tx == 0) mu[c0 + ty + 16 * a] = hyp[2 * d + 1] + double(v);
+    if (tx == 0) mu[c0 + ty + 16 * a] = hyp[2 * d + 1] + double(s2) * double(v);
   }
 }
 
@@ -946,6 +965,12 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
   const float r = x - __uint_as_float(hi);
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+// two floats -> one word of binary16 (round to nearest even), `lo` at the lower address
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+  uint32_t u;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(hi), "f"(lo));
+  return u;
 }
 // cvt.rna.tf32.f32 of a finite value with two integer-pipe instructions (round to nearest, ties away:
 // add half an ulp of the 13 dropped bits, clear them).  The conversion instruction runs on the XU pipe,
@@ -1020,7 +1045,7 @@ template <typename T1, int KS, bool MATERN>   // KS = ceil((d+2)/8) k-steps
 __global__ void __launch_bounds__(256)
 k_kstar_mma2(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const uint32_t* __restrict__ Xhi,
              const uint32_t* __restrict__ Xlo, int64_t np, const double* __restrict__ hyp,
-             const float* __restrict__ alpha32, float* __restrict__ Ks, double* __restrict__ mu) {
+             const float* __restrict__ alpha32, __half* __restrict__ Ks, double* __restrict__ mu) {
   constexpr int DK = KS * 8;
   constexpr int LS = 4 * ((DK / 4 + 1) | 1);   // LS/4 odd: ldmatrix rows hit distinct 16-byte bank groups
   extern __shared__ __align__(16) uint32_t msm2[];
@@ -1032,7 +1057,6 @@ k_kstar_mma2(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const uint32
   const float eps = MATERN ? float(h.pairwise_eps) : 0.f;
   const float s2 = float(hyp[2 * d]);
   const float kLog2e = 1.4426950408889634f;
-  const float l2s2 = __log2f(s2);
   const int64_t row0 = int64_t(blockIdx.x) * 128 + warp * 16;   // this warp's 16 candidates
 
   // A fragments: a0 (g, t), a1 (g+8, t), a2 (g, t+4), a3 (g+8, t+4) per k-step; a' = xq/l - eps
@@ -1059,8 +1083,8 @@ k_kstar_mma2(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const uint32
     an0 += __shfl_xor_sync(0xffffffffu, an0, 2);
     an1 += __shfl_xor_sync(0xffffffffu, an1, 1);
     an1 += __shfl_xor_sync(0xffffffffu, an1, 2);
-    const float R0 = MATERN ? an0 : fmaf(-0.5f * kLog2e, an0, l2s2);
-    const float R1 = MATERN ? an1 : fmaf(-0.5f * kLog2e, an1, l2s2);
+    const float R0 = MATERN ? an0 : -0.5f * kLog2e * an0;      // correlations: no sigma^2 in the exponent
+    const float R1 = MATERN ? an1 : -0.5f * kLog2e * an1;
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
@@ -1093,8 +1117,8 @@ k_kstar_mma2(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const uint32
       unsigned(((lane & 7) * LS + ((lane >> 3) & 1) * 4) * 4);
   float m0 = 0.f, m1 = 0.f;   // mu partials of rows g, g+8
   const int ntile = int(np / 64);
-  float* o0 = Ks + (row0 + g) * np + 2 * t;
-  float* o1 = Ks + (row0 + g + 8) * np + 2 * t;
+  __half* o0 = Ks + (row0 + g) * np + 2 * t;
+  __half* o1 = Ks + (row0 + g + 8) * np + 2 * t;
   for (int tl = 0; tl < ntile; ++tl) {
     const int buf = tl & 1;
     asm volatile("cp.async.wait_group 0;");
@@ -1117,20 +1141,17 @@ k_kstar_mma2(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const uint32
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         if (!MATERN) {
-          v[e] = ex2_approx(fminf(c[e], l2s2));
+          v[e] = ex2_approx(fminf(c[e], 0.f));
         } else {
           const float r = 2.2360679775f * sqrtf(fmaxf(c[e], 0.f));
-          v[e] = s2 * fmaf(r, fmaf(r, 1.f / 3.f, 1.f), 1.f) * ex2_approx(-kLog2e * r);
+          v[e] = fmaf(r, fmaf(r, 1.f / 3.f, 1.f), 1.f) * ex2_approx(-kLog2e * r);
         }
       }
       const float2 al = *reinterpret_cast<const float2*>(ap + nt * 8);
       m0 = fmaf(v[0], al.x, fmaf(v[1], al.y, m0));
       m1 = fmaf(v[2], al.x, fmaf(v[3], al.y, m1));
-      uint32_t u[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) u[e] = round_tf32_bits(v[e]);
-      *reinterpret_cast<uint2*>(o0 + nt * 8) = make_uint2(u[0], u[1]);
-      *reinterpret_cast<uint2*>(o1 + nt * 8) = make_uint2(u[2], u[3]);
+      *reinterpret_cast<uint32_t*>(o0 + nt * 8) = pack_half2(v[0], v[1]);
+      *reinterpret_cast<uint32_t*>(o1 + nt * 8) = pack_half2(v[2], v[3]);
     }
     o0 += 64;
     o1 += 64;
@@ -1140,8 +1161,8 @@ k_kstar_mma2(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, const uint32
   m1 += __shfl_xor_sync(0xffffffffu, m1, 1);
   m1 += __shfl_xor_sync(0xffffffffu, m1, 2);
   if (t == 0) {
-    mu[row0 + g] = hyp[2 * d + 1] + double(m0);
-    mu[row0 + g + 8] = hyp[2 * d + 1] + double(m1);
+    mu[row0 + g] = hyp[2 * d + 1] + double(s2) * double(m0);
+    mu[row0 + g + 8] = hyp[2 * d + 1] + double(s2) * double(m1);
   }
 }
 
@@ -1251,7 +1272,7 @@ k_prescale_cand_umma(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, int6
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) an += __shfl_xor_sync(0xffffffffu, an, o);
-  const float R = matern ? an : fmaf(-0.5f * kLog2e, an, __log2f(float(hyp[2 * d])));
+  const float R = matern ? an : -0.5f * kLog2e * an;      // the producers emit correlations (no sigma^2)
   uint32_t* row = Aop + c * ktp;
   for (int k = lane; k < dk; k += 32) {
     float u = 0.f;
@@ -1379,7 +1400,6 @@ k_kstar_umma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const int row = quarter * 32 + lane;
     const uint32_t stg = sbase + uint32_t(3 * op_bytes + ew * ku::OUT_BYTES);
     const float s2 = float(hyp[2 * d]);
-    const float l2s2 = __log2f(s2);
     const float kLog2e = 1.4426950408889634f;
     const double cmean = hyp[2 * d + 1];
     const uint32_t tlane = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(colq * 32);
@@ -1420,27 +1440,31 @@ k_kstar_umma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         acc = 0;
         acc_phase ^= 1;
       }
-      // values -> K*, mu partial, TF32 bits into the swizzled staging tile, TMA store
-      const uint32_t sdst = stg + uint32_t(lane * 128);
+      // values -> correlations, mu partial, binary16 pairs into the 64-byte-swizzled staging tile, TMA store
+      const uint32_t sdst = stg + uint32_t(lane * 64);
 #pragma unroll
-      for (int c4 = 0; c4 < 8; ++c4) {
+      for (int c8 = 0; c8 < 4; ++c8) {
         uint32_t u[4];
-        const float4 av = *reinterpret_cast<const float4*>(al + c4 * 4);
-        const float a4[4] = {av.x, av.y, av.z, av.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float x = __uint_as_float(r[c4 * 4 + e]);
-          float val;
-          if (!MATERN) {
-            val = ex2_approx(fminf(x, l2s2));
-          } else {
-            const float rr = 2.2360679775f * sqrtf(fmaxf(x, 0.f));
-            val = s2 * fmaf(rr, fmaf(rr, 1.f / 3.f, 1.f), 1.f) * ex2_approx(-kLog2e * rr);
+        for (int h = 0; h < 2; ++h) {
+          const float4 av = *reinterpret_cast<const float4*>(al + c8 * 8 + h * 4);
+          const float a4[4] = {av.x, av.y, av.z, av.w};
+          float cv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float x = __uint_as_float(r[c8 * 8 + h * 4 + e]);
+            if (!MATERN) {
+              cv[e] = ex2_approx(fminf(x, 0.f));
+            } else {
+              const float rr = 2.2360679775f * sqrtf(fmaxf(x, 0.f));
+              cv[e] = fmaf(rr, fmaf(rr, 1.f / 3.f, 1.f), 1.f) * ex2_approx(-kLog2e * rr);
+            }
+            m = fmaf(cv[e], a4[e], m);
           }
-          m = fmaf(val, a4[e], m);
-          u[e] = round_tf32_bits(val);
+          u[2 * h] = pack_half2(cv[0], cv[1]);
+          u[2 * h + 1] = pack_half2(cv[2], cv[3]);
         }
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdst + uint32_t((c4 ^ (lane & 7)) * 16)),
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdst + uint32_t((c8 ^ ((lane >> 1) & 3)) * 16)),
                      "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3])
                      : "memory");
       }
@@ -1456,7 +1480,8 @@ k_kstar_umma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         asm volatile("bar.sync 1, %0;" ::"n"(ku::EPI_WARPS * 32) : "memory");
         if (colq == 0)
           mu[int64_t(tile) * ku::BM + row] =
-              cmean + double(((m + mu_sh[tcount & 1][0][row]) + mu_sh[tcount & 1][1][row]) + mu_sh[tcount & 1][2][row]);
+              cmean + double(s2) * double(((m + mu_sh[tcount & 1][0][row]) + mu_sh[tcount & 1][1][row]) +
+                                          mu_sh[tcount & 1][2][row]);
         m = 0.f;
         tile += gridDim.x;
         ++tcount;
@@ -1580,7 +1605,6 @@ k_kstar_umma_stream(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const int row = quarter * 32 + lane;
     const uint32_t stg = sbase + uint32_t(ku::SSTAGES * stage_bytes + ew * ku::OUT_BYTES);
     const float s2 = float(hyp[2 * d]);
-    const float l2s2 = __log2f(s2);
     const float kLog2e = 1.4426950408889634f;
     const double cmean = hyp[2 * d + 1];
     const uint32_t tlane = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(colq * 32);
@@ -1621,27 +1645,31 @@ k_kstar_umma_stream(const __grid_constant__ CUtensorMap mapA, const __grid_const
         acc = 0;
         acc_phase ^= 1;
       }
-      // values -> K*, mu partial, TF32 bits into the swizzled staging tile, TMA store
-      const uint32_t sdst = stg + uint32_t(lane * 128);
+      // values -> correlations, mu partial, binary16 pairs into the 64-byte-swizzled staging tile, TMA store
+      const uint32_t sdst = stg + uint32_t(lane * 64);
 #pragma unroll
-      for (int c4 = 0; c4 < 8; ++c4) {
+      for (int c8 = 0; c8 < 4; ++c8) {
         uint32_t u[4];
-        const float4 av = *reinterpret_cast<const float4*>(al + c4 * 4);
-        const float a4[4] = {av.x, av.y, av.z, av.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float x = __uint_as_float(r[c4 * 4 + e]);
-          float val;
-          if (!MATERN) {
-            val = ex2_approx(fminf(x, l2s2));
-          } else {
-            const float rr = 2.2360679775f * sqrtf(fmaxf(x, 0.f));
-            val = s2 * fmaf(rr, fmaf(rr, 1.f / 3.f, 1.f), 1.f) * ex2_approx(-kLog2e * rr);
+        for (int h = 0; h < 2; ++h) {
+          const float4 av = *reinterpret_cast<const float4*>(al + c8 * 8 + h * 4);
+          const float a4[4] = {av.x, av.y, av.z, av.w};
+          float cv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float x = __uint_as_float(r[c8 * 8 + h * 4 + e]);
+            if (!MATERN) {
+              cv[e] = ex2_approx(fminf(x, 0.f));
+            } else {
+              const float rr = 2.2360679775f * sqrtf(fmaxf(x, 0.f));
+              cv[e] = fmaf(rr, fmaf(rr, 1.f / 3.f, 1.f), 1.f) * ex2_approx(-kLog2e * rr);
+            }
+            m = fmaf(cv[e], a4[e], m);
           }
-          m = fmaf(val, a4[e], m);
-          u[e] = round_tf32_bits(val);
+          u[2 * h] = pack_half2(cv[0], cv[1]);
+          u[2 * h + 1] = pack_half2(cv[2], cv[3]);
         }
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdst + uint32_t((c4 ^ (lane & 7)) * 16)),
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdst + uint32_t((c8 ^ ((lane >> 1) & 3)) * 16)),
                      "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3])
                      : "memory");
       }
@@ -1657,7 +1685,8 @@ k_kstar_umma_stream(const __grid_constant__ CUtensorMap mapA, const __grid_const
         asm volatile("bar.sync 1, %0;" ::"n"(ku::EPI_WARPS * 32) : "memory");
         if (colq == 0)
           mu[int64_t(tile) * ku::BM + row] =
-              cmean + double(((m + mu_sh[tcount & 1][0][row]) + mu_sh[tcount & 1][1][row]) + mu_sh[tcount & 1][2][row]);
+              cmean + double(s2) * double(((m + mu_sh[tcount & 1][0][row]) + mu_sh[tcount & 1][1][row]) +
+                                          mu_sh[tcount & 1][2][row]);
         m = 0.f;
         tile += gridDim.x;
         ++tcount;
@@ -1694,23 +1723,59 @@ static size_t kstar_fast_smem(int d) {
 // 16-column stage starting kk columns into the diagonal block only the first 256 - kk physical rows are non-zero and
 // the tensor core is given N = 256 - kk instead of 256 (k_vnorm_tf32_2sm: accumulator column c = physical row c in
 // every stage).
-__global__ void k_make_tf32(int64_t np, int64_t total, const double* __restrict__ in, float* __restrict__ out) {
+// binary16 copy of L^-1 for the panel: out[prow, col] = half(2^e linv[lrow, col]) with the rows of every 256-row block
+// in reverse order (see the panel's diagonal blocks), zero rows up to tf32_rows(n), and e chosen so that the largest
+// |entry| lands in [2^13, 2^14): the 10-bit mantissa is TF32's, the scaling keeps every entry that matters in the
+// normal range (an entry below 2^-28 of the largest is rounded with an absolute error of 2^-39 of the largest).
+// The scale lives behind the data: float words [0] = 2^-2e (what the panel's sums of squares are multiplied by),
+// [1] = 2^e, [2] = bits of max |entry| (scratch of the reduction).
+__global__ void k_linv_absmax(int64_t total, const double* __restrict__ in, uint32_t* __restrict__ out_bits) {
+  float m = 0.f;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x)
+    m = fmaxf(m, fabsf(static_cast<float>(in[i])));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits, __float_as_uint(m));   // non-negative floats order as uints
+}
+__global__ void k_linv_scale(float* __restrict__ sc) {
+  const float m = __uint_as_float(reinterpret_cast<const uint32_t*>(sc)[2]);
+  int e = 0;
+  if (m > 0.f && isfinite(m)) {
+    int ex;
+    frexpf(m, &ex);          // m = f 2^ex, f in [0.5, 1)
+    e = 14 - ex;             // 2^e m in [2^13, 2^14)
+  }
+  sc[0] = exp2f(float(-2 * e));
+  sc[1] = exp2f(float(e));
+}
+__global__ void k_make_f16(int64_t np, int64_t total, const double* __restrict__ in, const float* __restrict__ sc,
+                           __half* __restrict__ out) {
   int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < total) {
     const int64_t prow = i / np, col = i - prow * np;
     const int64_t lrow = (prow >> 8) * 256 + 255 - (prow & 255);
-    float f = lrow < np ? static_cast<float>(in[lrow * np + col]) : 0.f;
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(f));
-    out[i] = __uint_as_float(u);
+    const double f = lrow < np ? in[lrow * np + col] * double(sc[1]) : 0.0;
+    out[i] = __double2half(f);
   }
 }
 
 int64_t tf32_rows(int64_t n) { return ceil_div(padded(n), tf::BN) * tf::BN; }
 
+// the scale words of the binary16 L^-1 copy (see k_make_f16): right behind the rows x np halves
+static const float* linv_scale_ptr(const bbo_gp_state& s) {
+  return s.linv_tf32 + tf32_rows(s.n) * padded(s.n) / 2;
+}
+
 int make_tf32(int64_t n, const double* linv, float* out, cudaStream_t st) {
   const int64_t np = padded(n), total = tf32_rows(n) * np;
-  k_make_tf32<<<unsigned(ceil_div(total, 256)), 256, 0, st>>>(np, total, linv, out);
+  float* sc = out + total / 2;
+  BBO_CUDA_CHECK(cudaMemsetAsync(sc, 0, 4 * sizeof(float), st));
+  k_linv_absmax<<<unsigned(std::min<int64_t>(ceil_div(np * np, 256), 1184)), 256, 0, st>>>(
+      np * np, linv, reinterpret_cast<uint32_t*>(sc) + 2);
+  BBO_LAUNCH_CHECK();
+  k_linv_scale<<<1, 1, 0, st>>>(sc);
+  BBO_LAUNCH_CHECK();
+  k_make_f16<<<unsigned(ceil_div(total, 256)), 256, 0, st>>>(np, total, linv, sc, reinterpret_cast<__half*>(out));
   BBO_LAUNCH_CHECK();
   return BBO_OK;
 }
@@ -1719,10 +1784,10 @@ int make_tf32(int64_t n, const double* linv, float* out, cudaStream_t st) {
 // host side
 // ------------------------------------------------------------------------------------------
 // TF32 scratch layout inside ScoreWorkspace::tf32:
-//   Ks[2]  (qp, np) float32  double-buffered K* chunk      mu1 (qp) float64  second mu buffer
+//   Ks[2]  (qp, np) binary16 double-buffered K* chunk      mu1 (qp) float64  second mu buffer
 //   Xs     (np, d)  float32  pre-scaled training inputs    alpha32 (np) float32
 struct Tf32Scratch {
-  float* Ks[2];
+  __half* Ks[2];
   double* mu[3];     // K* producers write mu of chunk i into mu[i % 3] (selection of chunk i runs up to two chunks later)
   float* Xs;
   float* bnorm;
@@ -1739,7 +1804,7 @@ static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 size_t score_tf32_extra_bytes(int64_t n, int64_t d, int64_t qp) {
   const int64_t np = padded(n);
-  return 2 * align256(size_t(qp) * np * sizeof(float)) + 2 * align256(size_t(qp) * sizeof(double)) +
+  return 2 * align256(size_t(qp) * np * sizeof(__half)) + 2 * align256(size_t(qp) * sizeof(double)) +
          align256(size_t(np) * d * sizeof(float)) + 2 * align256(size_t(np) * sizeof(float)) +
          2 * align256(size_t(np) * (d + 16) * sizeof(uint32_t)) +
          align256(size_t(qp) * 2 * (d + 16) * sizeof(uint32_t)) +
@@ -1750,10 +1815,10 @@ size_t score_tf32_extra_bytes(int64_t n, int64_t d, int64_t qp) {
 static Tf32Scratch carve(const ScoreWorkspace& w, int64_t d) {
   Tf32Scratch t;
   char* p = static_cast<char*>(w.tf32);
-  const size_t kb = align256(size_t(w.qp) * w.np * sizeof(float));
-  t.Ks[0] = reinterpret_cast<float*>(p);
+  const size_t kb = align256(size_t(w.qp) * w.np * sizeof(__half));
+  t.Ks[0] = reinterpret_cast<__half*>(p);
   p += kb;
-  t.Ks[1] = reinterpret_cast<float*>(p);
+  t.Ks[1] = reinterpret_cast<__half*>(p);
   p += kb;
   t.mu[0] = w.mu;
   t.mu[1] = reinterpret_cast<double*>(p);
@@ -1800,19 +1865,28 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2-D float32 row-major (rows, cols) tensor, box = (box_rows, 32 floats), 128-byte swizzle
-static int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int box_rows, int box_k = tf::BK) {
+// row-major (rows, cols) tensor of 4-byte words or binary16 values; boxes of box_rows x box_k elements whose rows
+// are 128 bytes (SWIZZLE_128B) or 64 bytes (SWIZZLE_64B)
+static int make_map_bytes(CUtensorMap* m, const void* base, CUtensorMapDataType dt, int esize, int64_t rows,
+                          int64_t cols, int box_rows, int box_k) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return cuda_fail(cudaErrorNotSupported, "cudaGetDriverEntryPoint(cuTensorMapEncodeTiled)");
+  if (box_k * esize != 128 && box_k * esize != 64) return BBO_ERR_BAD_ARG;
   cuuint64_t gdim[2] = {cuuint64_t(cols), cuuint64_t(rows)};
-  cuuint64_t gstr[1] = {cuuint64_t(cols) * sizeof(float)};
+  cuuint64_t gstr[1] = {cuuint64_t(cols) * cuuint64_t(esize)};
   cuuint32_t box[2] = {cuuint32_t(box_k), cuuint32_t(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_k == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(m, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   box_k * esize == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return cuda_fail(cudaErrorInvalidValue, "cuTensorMapEncodeTiled");
   return BBO_OK;
+}
+static int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int box_rows, int box_k = tf::BK) {
+  return make_map_bytes(m, base, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, rows, cols, box_rows, box_k);
+}
+static int make_map(CUtensorMap* m, const __half* base, int64_t rows, int64_t cols, int box_rows, int box_k) {
+  return make_map_bytes(m, base, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, rows, cols, box_rows, box_k);
 }
 
 // auxiliary stream + events of the K* / panel software pipeline (created once per device)
@@ -1903,7 +1977,7 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
     if (rc != BBO_OK) return rc;
     rc = make_map(&mapB, reinterpret_cast<const float*>(t.Bop), np, ktp, ku::BN, ku::BOXK);
     if (rc != BBO_OK) return rc;
-    rc = make_map(&mapO, t.Ks[buf], qc_pad, np, 32, ku::BOXK);
+    rc = make_map(&mapO, t.Ks[buf], qc_pad, np, 32, 32);        // 32 candidates x 32 binary16 values (64-byte rows)
     if (rc != BBO_OK) return rc;
     const int tiles = int(qc_pad / ku::BM);
     const int grid = tiles < sm_count() ? tiles : sm_count();
@@ -2033,9 +2107,10 @@ static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
   }
   const bool use_cluster = pair && clus && (qc_pad / tf::BM) % 2 == 0;
   CUtensorMap mapA, mapB;
-  int rc = make_map(&mapA, t.Ks[buf], qc_pad, np, tf::BM, pair ? tfp::BK : tf::BK);
+  int rc = make_map(&mapA, t.Ks[buf], qc_pad, np, tf::BM, tfp::BK);
   if (rc != BBO_OK) return rc;
-  rc = make_map(&mapB, s.linv_tf32, tf32_rows(s.n), np, use_cluster ? tf::BN / 2 : tf::BN, pair ? tfp::BK : tf::BK);
+  rc = make_map(&mapB, reinterpret_cast<const __half*>(s.linv_tf32), tf32_rows(s.n), np,
+                use_cluster ? tf::BN / 2 : tf::BN, tfp::BK);
   if (rc != BBO_OK) return rc;
   const int64_t tiles = qc_pad / tf::BM;
   const int64_t nblk = ceil_div(np, tf::BN);
@@ -2046,6 +2121,9 @@ static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
   if (nblk < 2) nsplit = 1;
   *nsplit_out = 4;   // k_acq always sums the four slots
   *vpart_out = vpart;
+  const double* hyp = s.hyp;
+  const int d_i = s.h.d;
+  const float* lscale = linv_scale_ptr(s);
   prof_begin(kProfTf32, st);
   if (use_cluster) {
     cudaLaunchConfig_t cfg = {};
@@ -2110,7 +2188,8 @@ static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
       cfg.gridDim = dim3(unsigned(2 * nc), 1);
       const int* sc = ax->sched[slot];
       double* vp32 = t.vp32[buf];
-      BBO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_vnorm_tf32_2sm<true>, mapA, mapB, np_i, qp_i, vp32, shrink, sc, maxj));
+      BBO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_vnorm_tf32_2sm<true>, mapA, mapB, np_i, qp_i, vp32, shrink, sc, maxj,
+                                        hyp, d_i, lscale));
       {
         std::lock_guard<std::mutex> lock(g_aux_mutex);
         BBO_CUDA_CHECK(cudaEventRecord(ax->used[slot], st));
@@ -2119,10 +2198,10 @@ static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
       *vpart_out = vp32;
     } else
       BBO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_vnorm_tf32_2sm<false>, mapA, mapB, np_i, qp_i, vp, shrink,
-                                        static_cast<const int*>(nullptr), 0));
+                                        static_cast<const int*>(nullptr), 0, hyp, d_i, lscale));
   } else
     k_vnorm_tf32_pair<1><<<dim3(unsigned(tiles), unsigned(nsplit)), tf::THREADS, tfp::SMEM_BYTES, st>>>(
-        mapA, mapB, int(np), w.qp, vpart);
+        mapA, mapB, int(np), w.qp, vpart, hyp, d_i, lscale);
   BBO_LAUNCH_CHECK();
   prof_end(kProfTf32, st);
   return BBO_OK;

@@ -28,13 +28,16 @@ TOL = 1e-3
     (200, 4, 1000, O.RBF),          # tcgen05 K* producer: one 32-word operand box (3 dk = 24)
     (300, 12, 1500, O.MATERN52),    # two boxes (3 dk = 48)
     (400, 28, 40000, O.MATERN52),   # three full boxes (3 dk = 96), persistent CTAs with > 1 tile each
+    (1500, 24, 9000, O.RBF),        # six 256-row blocks, the last one partial
+    (2040, 13, 70000, O.MATERN52),  # np = 2048, several work-list items per CTA pair
+    (640, 8, 3000, O.RBF),          # one operand box, three 256-row blocks (last partial)
 ])
 def test_tf32_posterior_and_selection(n, d, q, kind, cuda_device):
     import bbo_b200 as B
     # d = 4 with length scales ~0.8 makes K ill-conditioned (cond 1e6, sum |alpha| = 2e5), so that the ~5e-7 relative
     # error of a 3xTF32 K* value, common to every TF32-mode producer, alone exceeds the 1e-3 gate on mu = k* . alpha:
     # shorter scales and more noise there (cond < 1e2)
-    small_d = d < 12
+    small_d = d < 16
     p, X, y = synth_problem(1000 + n, n, d, kind=kind, noise=1e-2 if small_d else 1e-4,
                             ls_mean=-2.0 if small_d else 0.2)
     Xq = np.random.default_rng(n).random((q, d))
@@ -88,6 +91,32 @@ def test_tf32_matches_fp64_mode_statistically(cuda_device):
     assert np.abs(err).max() < 1e-3
     assert abs(err.mean()) < 0.25 * np.abs(err).max()
     assert np.abs(np_(mu32 - mu64)).max() < 1e-3
+
+
+@pytest.mark.parametrize("raw_var,noise", [(6.0, 1e-8), (-7.0, 1e-6), (0.2, 1e-4)])
+def test_tf32_operand_range(raw_var, noise, cuda_device):
+    """The panel's operands travel as binary16: correlations K*/s2 in (0, 1] and L^-1 times a power of two chosen from
+    its largest entry (k_make_f16).  Neither a large signal variance (s2 ~ 400) nor a tiny one (s2 ~ 1e-3), nor
+    1/sqrt(noise) = 1e4 on the diagonal of L^-1, may cost accuracy: same gates as above, relative to the prior."""
+    import bbo_b200 as B
+    n, d, q = 900, 20, 6000
+    p, X, y = synth_problem(4242, n, d, kind=O.RBF, noise=noise, ls_mean=-0.8)
+    p.raw_variance = raw_var
+    Xq = np.random.default_rng(9).random((q, d))
+    gp = gp_from_params(p, X, y)
+    acq = B.UCB()
+    _, _, mu, var, _ = gp.score_pool(torch.as_tensor(Xq).cuda(), acq, 4, precision="tf32", return_all=True)
+    _, _, omu, ovar, _ = O.score_pool(p, X, y, Xq, "ucb", 0.0, k=4)
+    prior = float(O.softplus(p.raw_variance)) + p.noise
+    assert np.max(np.abs(np_(var) - ovar.numpy())) <= TOL * prior
+    assert np.max(np.abs(np_(mu) - omu.numpy())) <= TOL * max(1.0, np.abs(omu.numpy()).max())
+    # the scale words behind the binary16 copy: 2^-2e and 2^e with 2^e max|L^-1| in [2^13, 2^14)
+    lt = gp._state["linv_tf32"].reshape(-1)
+    sc = lt[lt.numel() // 2: lt.numel() // 2 + 3].cpu()
+    e2 = float(sc[1])
+    assert e2 > 0 and float(np.log2(e2)).is_integer() and abs(float(sc[0]) * e2 * e2 - 1.0) < 1e-6
+    amax = float(gp._state["linv"].abs().max())
+    assert 2.0 ** 13 <= amax * e2 < 2.0 ** 14
 
 
 def test_tf32_alternative_kernels_agree(cuda_device):
