@@ -261,6 +261,7 @@ k_acq_elem(bbo_acq a, const T* __restrict__ mu, const T* __restrict__ sd, T* __r
 // k selection rounds over the kSeg (score, index) pairs staged in shared memory: per round a warp-shuffle
 // arg-max with the (score desc, index asc) key, then thread 0 combines the 8 warps, emits the winner and
 // retires it.  Must be called by all 256 threads after the staging stores (it starts with a barrier).
+template <int N = kSeg>
 __device__ __forceinline__ void select_rounds(double* ss, int64_t* si, double* ws, int64_t* wi, int* wp, int k,
                                               double* __restrict__ out_s, int64_t* __restrict__ out_i) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -270,7 +271,7 @@ __device__ __forceinline__ void select_rounds(double* ss, int64_t* si, double* w
     int64_t bi = -1;
     int bp = -1;
 #pragma unroll
-    for (int u = 0; u < kSeg / 256; ++u) {
+    for (int u = 0; u < N / 256; ++u) {
       const int p = tid + u * 256;
       if (better(ss[p], si[p], bs, bi)) {
         bs = ss[p];
@@ -443,35 +444,38 @@ k_topk_merge_running(const double* __restrict__ as, const int64_t* __restrict__ 
 // The result is the same set as before: the K best by (score desc, index asc) of a set does not depend on the
 // order in which its members arrive, so atomics may order the survivor buffer freely.
 // ------------------------------------------------------------------------------------------
-constexpr int kFilterLocal = 64;   // more passing candidates than this in one block -> local arg-max rounds
+// Two kernels: k_acq_eval (128 threads, two candidates each, no staging arrays) is light enough to run NEXT TO the
+// persistent tensor-core kernels that hold every SM -- it used to be a 19-block, 33 KB-smem kernel that waited for
+// them and then delayed the next panel by its own 43 us.  A block (256 candidates) with more than kEvalLocal passing
+// candidates parks its scores in `score_tmp` and raises its flag; k_filter_heavy (one block per kSeg candidates,
+// exits at once when no flag is up) reduces the flagged blocks of its segment to their K best.
+constexpr int kEvalThreads = 128, kEvalPer = 2, kEvalBlock = kEvalThreads * kEvalPer;
+constexpr int kEvalLocal = 32;     // more passing candidates than this in one block -> k_filter_heavy
+constexpr int kFilterSlack = (kSeg / kEvalBlock - 1) * kEvalLocal;   // survivors of a segment: <= K + this
 
-__global__ void __launch_bounds__(256)
-k_acq_filter(bbo_gp_hyper h, bbo_acq a, int clamp_var, const double* __restrict__ hyp,
-             const double* __restrict__ mu, const double* __restrict__ vpart, int nsplit, int64_t qc_pad, int64_t qc,
-             int64_t base, int K, const double* __restrict__ run_s, const int64_t* __restrict__ run_i,
-             double* __restrict__ mu_out, double* __restrict__ var_out, double* __restrict__ score_out,
-             int32_t* __restrict__ nan_count, double* __restrict__ surv_s, int64_t* __restrict__ surv_i,
-             int* __restrict__ surv_count) {
-  __shared__ double ss[kSeg];
-  __shared__ int64_t si[kSeg];
-  __shared__ double ws[8];
-  __shared__ int64_t wi[8];
-  __shared__ int wp[8];
-  __shared__ int s_base;
+// counters[0] = survivors, counters[1] = flagged blocks
+__global__ void __launch_bounds__(kEvalThreads)
+k_acq_eval(bbo_gp_hyper h, bbo_acq a, int clamp_var, const double* __restrict__ hyp, const double* __restrict__ mu,
+           const double* __restrict__ vpart, int nsplit, int64_t qc_pad, int64_t qc, int64_t base, int K,
+           const double* __restrict__ run_s, const int64_t* __restrict__ run_i, double* __restrict__ mu_out,
+           double* __restrict__ var_out, double* __restrict__ score_out, int32_t* __restrict__ nan_count,
+           double* __restrict__ surv_s, int64_t* __restrict__ surv_i, int* __restrict__ counters,
+           double* __restrict__ score_tmp, int* __restrict__ heavy) {
+  __shared__ int wp[kEvalThreads / 32];
   const int tid = threadIdx.x;
-  const int64_t s0 = int64_t(blockIdx.x) * kSeg;
+  const int64_t s0 = int64_t(blockIdx.x) * kEvalBlock;
   const double eps = h.kind == BBO_KERNEL_MATERN52 ? h.pairwise_eps : 0.0;
   const double kxx = hyp[2 * h.d] * kernel_from_s(h.kind, double(h.d) * eps * eps);
   const double thr_s = run_s[K - 1];
   const int64_t thr_i = run_i[K - 1];
-  double sc[kSeg / 256];
-  int64_t ix[kSeg / 256];
+  double sc[kEvalPer];
+  bool pass[kEvalPer];
   int nans = 0, npass = 0;
 #pragma unroll
-  for (int u = 0; u < kSeg / 256; ++u) {
-    const int64_t c = s0 + tid + 256 * u;
-    sc[u] = -INFINITY;
-    ix[u] = -1;
+  for (int u = 0; u < kEvalPer; ++u) {
+    const int64_t c = s0 + tid + kEvalThreads * u;
+    sc[u] = nan("");
+    pass[u] = false;
     if (c < qc) {
       const double vn = sum_vpart(vpart, nsplit, qc_pad, c);
       double var = kxx - vn + h.noise;
@@ -484,14 +488,13 @@ k_acq_filter(bbo_gp_hyper h, bbo_acq a, int clamp_var, const double* __restrict_
       if (v != v) ++nans;
       else if (better(v, base + c, thr_s, thr_i)) {
         sc[u] = v;
-        ix[u] = base + c;
+        pass[u] = true;
         ++npass;
       }
     }
   }
   if (nans && nan_count) atomicAdd(nan_count, nans);
-  if (__syncthreads_count(npass > 0) == 0) return;   // nothing in this segment beats the running list (the usual case)
-  // block-wide number of passing candidates
+  if (__syncthreads_count(npass > 0) == 0) return;   // nothing in this block beats the running list (the usual case)
   int cnt = npass;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
@@ -499,26 +502,65 @@ k_acq_filter(bbo_gp_hyper h, bbo_acq a, int clamp_var, const double* __restrict_
   __syncthreads();
   int block_pass = 0;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) block_pass += wp[w];
-  __syncthreads();                              // wp is reused by select_rounds below
-  if (block_pass <= kFilterLocal) {
+  for (int w = 0; w < kEvalThreads / 32; ++w) block_pass += wp[w];
+  if (block_pass <= kEvalLocal) {
 #pragma unroll
-    for (int u = 0; u < kSeg / 256; ++u)
-      if (ix[u] >= 0) {
-        const int p = atomicAdd(surv_count, 1);
+    for (int u = 0; u < kEvalPer; ++u)
+      if (pass[u]) {
+        const int p = atomicAdd(counters, 1);
         surv_s[p] = sc[u];
-        surv_i[p] = ix[u];
+        surv_i[p] = base + s0 + tid + kEvalThreads * u;
       }
     return;
   }
-  // many candidates pass: this block's own K best (arg-max rounds over the staged segment)
+  // many candidates pass (first chunks, or a pool sorted by score): park the scores (NaN = did not pass)
 #pragma unroll
-  for (int u = 0; u < kSeg / 256; ++u) {
-    ss[tid + 256 * u] = sc[u];
-    si[tid + 256 * u] = ix[u];
+  for (int u = 0; u < kEvalPer; ++u) {
+    const int64_t c = s0 + tid + kEvalThreads * u;
+    if (c < qc) score_tmp[c] = sc[u];
   }
-  const int kk = block_pass < K ? block_pass : K;
-  if (tid == 0) s_base = atomicAdd(surv_count, kk);
+  if (tid == 0) {
+    heavy[blockIdx.x] = 1;
+    atomicAdd(counters + 1, 1);
+  }
+}
+
+// grid = segments of kSeg candidates; a segment's flagged blocks -> their K best by arg-max rounds -> survivor list
+__global__ void __launch_bounds__(256)
+k_filter_heavy(int64_t qc, int64_t base, int K, const double* __restrict__ score_tmp, int* __restrict__ heavy,
+               double* __restrict__ surv_s, int64_t* __restrict__ surv_i, int* __restrict__ counters) {
+  if (counters[1] == 0) return;                 // no flag anywhere in this chunk (the usual case)
+  __shared__ double ss[kSeg];
+  __shared__ int64_t si[kSeg];
+  __shared__ double ws[8];
+  __shared__ int64_t wi[8];
+  __shared__ int wp[8];
+  __shared__ int s_base;
+  const int tid = threadIdx.x;
+  const int64_t s0 = int64_t(blockIdx.x) * kSeg;
+  constexpr int kSub = kSeg / kEvalBlock;       // blocks of k_acq_eval per segment (thread tid + 256 u is in block u)
+  const int64_t nsub = (qc + kEvalBlock - 1) / kEvalBlock;
+  int total = 0;
+#pragma unroll
+  for (int u = 0; u < kSub; ++u) {
+    const int64_t sub = int64_t(blockIdx.x) * kSub + u, c = s0 + tid + 256 * u;
+    double v = -INFINITY;
+    int64_t ix = -1;
+    if (sub < nsub && heavy[sub] != 0 && c < qc) {
+      const double t = score_tmp[c];
+      if (t == t) {
+        v = t;
+        ix = base + c;
+      }
+    }
+    ss[tid + 256 * u] = v;
+    si[tid + 256 * u] = ix;
+    total += __syncthreads_count(ix >= 0);
+  }
+  if (total == 0) return;
+  if (tid < kSub && int64_t(blockIdx.x) * kSub + tid < nsub) heavy[int64_t(blockIdx.x) * kSub + tid] = 0;
+  const int kk = total < K ? total : K;
+  if (tid == 0) s_base = atomicAdd(counters, kk);
   __syncthreads();
   select_rounds(ss, si, ws, wi, wp, kk, surv_s + s_base, surv_i + s_base);
 }
@@ -527,15 +569,19 @@ k_acq_filter(bbo_gp_hyper h, bbo_acq a, int clamp_var, const double* __restrict_
 __global__ void __launch_bounds__(256)
 k_merge_survivors(const double* __restrict__ surv_s, const int64_t* __restrict__ surv_i, int* __restrict__ surv_count,
                   int K, double* __restrict__ run_s, int64_t* __restrict__ run_i) {
-  __shared__ double ss[kSeg];
-  __shared__ int64_t si[kSeg];
+  constexpr int kCap = 1024;       // staged entries: 16 KB, so that the block fits beside a persistent panel CTA
+  __shared__ double ss[kCap];
+  __shared__ int64_t si[kCap];
   __shared__ double ws[8];
   __shared__ int64_t wi[8];
   __shared__ int wp[8];
   const int tid = threadIdx.x;
   const int c = *surv_count;
   __syncthreads();
-  if (tid == 0) *surv_count = 0;
+  if (tid == 0) {
+    surv_count[0] = 0;
+    surv_count[1] = 0;
+  }
   if (c == 0) return;
   if (K + c <= 512) {
     // ranking merge: position of an element = number of elements that beat it (keys are distinct: indices are)
@@ -574,9 +620,9 @@ k_merge_survivors(const double* __restrict__ surv_s, const int64_t* __restrict__
     return;
   }
   // many survivors (first chunks): arg-max rounds over [running list | batch of survivors], batch after batch
-  for (int b0 = 0; b0 < c; b0 += kSeg - K) {
-    const int nb = (c - b0 < kSeg - K) ? c - b0 : kSeg - K;
-    for (int p = tid; p < kSeg; p += 256) {
+  for (int b0 = 0; b0 < c; b0 += kCap - K) {
+    const int nb = (c - b0 < kCap - K) ? c - b0 : kCap - K;
+    for (int p = tid; p < kCap; p += 256) {
       double sc = -INFINITY;
       int64_t ix = -1;
       if (p < K) {
@@ -589,7 +635,7 @@ k_merge_survivors(const double* __restrict__ surv_s, const int64_t* __restrict__
       ss[p] = sc;
       si[p] = ix;
     }
-    select_rounds(ss, si, ws, wi, wp, K, run_s, run_i);
+    select_rounds<kCap>(ss, si, ws, wi, wp, K, run_s, run_i);
     __syncthreads();
   }
 }
@@ -701,7 +747,8 @@ size_t ScoreWorkspace::bytes(int64_t n, int64_t d, int64_t q_chunk, int precisio
   const size_t ks = (tf32 && !want_full) ? 0 : size_t(qp) * np;   // TF32 keeps K* in float32
   size_t doubles = ks * (want_full ? 2 : 1)  // Ks (+V)
                    + size_t(kMaxSplit) * qp + 2 * size_t(qp)  // vpart, mu, score
-                   + 2 * (size_t(256) * (nblk + 1) + 256) * 2 + 32;  // two (score,index) lists + survivor counter
+                   + 2 * (size_t(512) * (nblk + 1) + 256) * 2     // two (score,index) lists
+                   + 32 + size_t(qp) / 512 + 8;                   // survivor counters + one flag per 256 candidates
   size_t extra = 0;
   if (tf32) extra = score_tf32_extra_bytes(n, d, qp);
   if (precision == BBO_PREC_TF32_REFINE) extra += refine_bytes(np, d);
@@ -727,7 +774,7 @@ int ScoreWorkspace::bind(void* ws, size_t ws_bytes, int64_t n, int64_t d, int64_
   score = q;
   q += qp;
   const int64_t nblk = ceil_div(qp, kSeg);
-  list_len = int64_t(256) * (nblk + 1) + 256;
+  list_len = int64_t(512) * (nblk + 1) + 256;
   la_s = q;
   q += list_len;
   lb_s = q;
@@ -736,8 +783,8 @@ int ScoreWorkspace::bind(void* ws, size_t ws_bytes, int64_t n, int64_t d, int64_
   q += list_len;
   lb_i = reinterpret_cast<int64_t*>(q);
   q += list_len;
-  surv_count = reinterpret_cast<int*>(q);
-  q += 32;
+  surv_count = reinterpret_cast<int*>(q);       // [0] survivors, [1] flagged blocks, [64 ..] the flags
+  q += 32 + size_t(qp) / 512 + 8;
   tf32 = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(q) + 255) & ~uintptr_t(255));
   refine = nullptr;
   if (precision == BBO_PREC_TF32_REFINE)
@@ -1123,7 +1170,7 @@ int gp_score_pool(const bbo_gp_state& s, const bbo_acq& acq, int precision, cons
   ScoreWorkspace w;
   rc = w.bind(ws, ws_bytes, s.n, s.h.d, q_chunk, precision, false);
   if (rc != BBO_OK) return rc;
-  BBO_CUDA_CHECK(cudaMemsetAsync(w.surv_count, 0, sizeof(int), st));
+  BBO_CUDA_CHECK(cudaMemsetAsync(w.surv_count, 0, (64 + size_t(w.qp) / 256 + 1) * sizeof(int), st));
   RefineScratch r{};
   const int m = refine ? refine_shortlist_len(k) : 0, kseg = refine ? refine_kseg(k) : 0;
   if (refine) {
@@ -1147,12 +1194,15 @@ int gp_score_pool(const bbo_gp_state& s, const bbo_acq& acq, int precision, cons
     const int K = refine ? m : k;
     double* run_s = refine ? r.sh_s : topk_s;
     int64_t* run_i = refine ? r.sh_i : topk_i;
-    if (!unfused && !rounds_only && nb * int64_t(K > kFilterLocal ? K : kFilterLocal) <= w.list_len) {
+    if (!unfused && !rounds_only && nb * int64_t(K + kFilterSlack) <= w.list_len) {
       // threshold filter (default): only candidates that beat the current last entry of the running list survive
-      k_acq_filter<<<unsigned(nb), 256, 0, sc>>>(
+      k_acq_eval<<<unsigned(ceil_div(qc, kEvalBlock)), kEvalThreads, 0, sc>>>(
           s.h, acq, tf32, s.hyp, mu_chunk, vpart, nsplit, w.qp, qc, index_offset + c0, K, run_s, run_i,
           mu_out ? mu_out + c0 : nullptr, var_out ? var_out + c0 : nullptr, score_out ? score_out + c0 : nullptr,
-          nan_count, w.la_s, w.la_i, w.surv_count);
+          nan_count, w.la_s, w.la_i, w.surv_count, w.score, w.surv_count + 64);
+      BBO_LAUNCH_CHECK();
+      k_filter_heavy<<<unsigned(nb), 256, 0, sc>>>(qc, index_offset + c0, K, w.score, w.surv_count + 64, w.la_s,
+                                                  w.la_i, w.surv_count);
       BBO_LAUNCH_CHECK();
       k_merge_survivors<<<1, 256, 0, sc>>>(w.la_s, w.la_i, w.surv_count, K, run_s, run_i);
       BBO_LAUNCH_CHECK();

@@ -1205,7 +1205,7 @@ constexpr int SSTAGES = 4;                         // streaming form: ring of (A
 constexpr int BSTAGES = 2, ACCS = 4;
 constexpr int EPI_WARPS = 16;
 constexpr int THREADS = 64 + 32 * EPI_WARPS;       // 576
-constexpr int OUT_BYTES = 32 * 128;                // staging tile: 32 candidates x 32 values
+constexpr int OUT_BYTES = 32 * 64;                 // staging tile: 32 candidates x 32 binary16 values
 constexpr int kMaxD = 30;                          // resident-A form
 constexpr int kMaxDStream = 126;                   // streaming form (dk = 8 ceil((d+2)/8) <= 128)
 static size_t smem_bytes(int nbox) {

@@ -1,0 +1,28 @@
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import bbo_b200 as B
+from bbo_b200.benchmarks import Ackley, make_observations
+from bbo_b200.pool import uniform_pool
+D, n = 20, 4096
+X, y = make_observations(Ackley(D), n, 20251019)
+cov = B.ScaleKernel(B.RBFKernel(ard_dim=D)).double()
+with torch.no_grad():
+    cov.base_kernel.lengthscale.fill_(float(np.log(np.expm1(0.5))))
+    cov.variance.fill_(float(np.log(np.expm1(1.0))))
+gp = B.CudaGP(torch.as_tensor(X), torch.as_tensor(y).reshape(-1, 1), B.ConstantMean().double(), cov, noise_variance=1e-4)
+acq = B.EI(float(y.max()))
+pool = uniform_pool(3, 0, 1 << 20, D)
+for prec in ("tf32+refine", "tf32"):
+    for _ in range(3):
+        gp.score_pool(pool, acq, 8, precision=prec)
+    torch.cuda.synchronize()
+    for rep in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            gp.score_pool(pool, acq, 8, precision=prec)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 5
+        print(prec, "ms/step", ms, "Mcand/s", (1 << 20) / ms / 1e3, flush=True)
