@@ -2,8 +2,13 @@
 //
 //   |L^-1 k*_c|^2 = sum_i ( sum_{j<=i} Ks[c,j] * Linv[i,j] )^2          (gp.py:80-81)
 //
+// Operands of the panel: TF32's 10-bit mantissa in binary16 containers -- Ks holds correlations K*/s2 in (0, 1],
+// Linv a power-of-two multiple of L^-1 (k_make_f16) -- multiplied by tcgen05 kind::f16 into float32 accumulators;
+// the epilogue's sums of squares are scaled back by s2^2 2^-2e (panel_factor).  Same rounding as kind::tf32 at
+// twice the rate and half the bytes.
+//
 // Kernels (one default per shape; the A/B generations of round 1 were removed in round 2):
-//   K* producers (cross-covariance of a chunk, TF32-rounded float32, fused with mu = c + K* alpha)
+//   K* producers (correlations of a chunk rounded to binary16, fused with mu = c + K* alpha from the float32 values)
 //     k_kstar_umma       d <= 30      tcgen05 kind::tf32, one 3xTF32 contraction over concatenated hi/lo rows,
 //                                     TMA operand loads, TMEM accumulator ring, TMA tensor stores
 //     k_kstar_umma_stream 30 < d <= 126 the same contraction with BOTH operands streamed in 32-word boxes
@@ -15,7 +20,7 @@
 //     k_vnorm_tf32_2sm<false>  one CTA pair per candidate tile pair, lock-step over the row pairs (n = 8192)
 //     k_vnorm_tf32_pair<1>     single-CTA form for chunks with an odd number of 128-candidate tiles
 //   warp roles of the panel kernels: warp 0 TMA producer (cp.async.bulk.tensor.2d, 64-byte swizzle, mbarrier
-//   ring), warp 1 one thread issuing tcgen05.mma kind::tf32 (M = 128 per CTA x N = 256 x K = 8, accumulators in
+//   ring), warp 1 one thread issuing tcgen05.mma kind::f16 (M = 128 per CTA x N = 256 x K = 16, accumulators in
 //   TMEM, two row blocks per K* stage), warps 2-5 epilogue (tcgen05.ld.32x32b.x32 -> square + row-sum).
 //   Triangular: row block nb only contracts k < (nb+1)*256.
 // SASS evidence: UTCHMMA(.2CTA) / UTMALDG / UTMASTG / LDTM / SYNCS (see profiles/).
@@ -2154,7 +2159,8 @@ static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
     // The persistent form trades the lock-step walk over the row pairs (which keeps the L^-1 blocks in flight few)
     // for K* strip reuse: it needs the whole TF32 L^-1 resident in L2 next to the strips (n = 4096: 67 of 126 MB).
     // At n = 8192 (268 MB) it was 9 % slower than the lock-step form, which therefore keeps the large problems.
-    const bool linv_fits_l2 = np * np * int64_t(sizeof(float)) <= (int64_t(80) << 20);
+    static const int64_t l2_mb = getenv("BBO_TF32_PERSIST_MAX_MB") ? atoll(getenv("BBO_TF32_PERSIST_MAX_MB")) : 80;
+    const bool linv_fits_l2 = np * np * int64_t(sizeof(__half)) <= (l2_mb << 20);
     if (two_sm && !no_persist && linv_fits_l2 && nblk >= 2 && nblk <= 32 && nc <= 96 &&
         int64_t(nc) * maxj <= kSchedInts) {
       // persistent form: one CTA pair per SM pair walks a work list (k_panel_schedule); one slot per row block

@@ -75,7 +75,9 @@ typedef enum bbo_kernel_kind { BBO_KERNEL_RBF = 0, BBO_KERNEL_MATERN52 = 1 } bbo
 typedef enum bbo_acq_kind { BBO_ACQ_EI = 0, BBO_ACQ_UCB = 1, BBO_ACQ_PI = 2 } bbo_acq_kind;
 /* arithmetic of the n^2 panel of the scoring pass.
  *   BBO_PREC_FP64         every candidate in float64 (DMMA)
- *   BBO_PREC_TF32         every candidate on the tcgen05 TF32 panel; scores are TF32-accurate (1e-3 class)
+ *   BBO_PREC_TF32         every candidate on the tcgen05 panel with 10-bit-mantissa operands (TF32's mantissa;
+ *                         stored in binary16 containers: correlations (K* divided by s2) and a power-of-two multiple of L^-1)
+ *                         and float32 accumulation; scores are TF32-accurate (1e-3 class)
  *   BBO_PREC_TF32_REFINE  the TF32 pass only builds a short-list of bbo_refine_shortlist(k) candidates by TF32
  *                         score; the short-list is re-scored by the float64 kernels and the k best BY FLOAT64
  *                         SCORE are returned, so the returned scores are float64-exact and the selection equals
@@ -215,13 +217,16 @@ typedef struct bbo_gp_state {
   const double* hyp;      /* (2d+2) */
   const double* linv;     /* (np, np) from bbo_gp_factorize */
   const double* alpha;    /* (np) */
-  const float* linv_tf32; /* (bbo_tf32_rows(n), np) float32 copy of linv rounded to TF32; only
-                             read when precision == BBO_PREC_TF32; see bbo_gp_make_tf32 */
+  const float* linv_tf32; /* bbo_tf32_rows(n) * np floats of storage filled by bbo_gp_make_tf32 (opaque: the
+                             10-bit-mantissa copy of linv the tensor-core panel reads); only read when
+                             precision != BBO_PREC_FP64 */
 } bbo_gp_state;
 
-/* float32 copy of linv rounded to TF32 (round-to-nearest) for the TF32 scoring mode:
- * linv_tf32_dev is (bbo_tf32_rows(n), np) -- np rows of data followed by zero rows up to a
- * multiple of 256, so that every TMA box of the tensor-core panel is in bounds.           */
+/* Copy of linv for the TF32 scoring mode, rounded to nearest at TF32's 10-bit mantissa.  The caller provides
+ * bbo_tf32_rows(n) * np floats; the library lays out, in the first half, (bbo_tf32_rows(n), np) binary16 values
+ * 2^e linv (np rows of data followed by zero rows up to a multiple of 256, so that every TMA box of the
+ * tensor-core panel is in bounds; e puts the largest |entry| in [2^13, 2^14)) and right behind them the float
+ * words 2^-2e, 2^e.  The layout is private to the library; only the size is part of the contract.           */
 int64_t bbo_tf32_rows(int64_t n);
 int bbo_gp_make_tf32(int64_t n, const double* linv_dev, float* linv_tf32_dev, void* stream);
 
