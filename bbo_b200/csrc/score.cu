@@ -565,18 +565,50 @@ k_filter_heavy(int64_t qc, int64_t base, int K, const double* __restrict__ score
   select_rounds(ss, si, ws, wi, wp, kk, surv_s + s_base, surv_i + s_base);
 }
 
-// Merge the survivors of one chunk into the running list (K entries, sorted) and reset the counter.  One block.
+constexpr int kMergeCap = 1024;    // staged entries: 16 KB, so that a merge block fits beside a persistent panel CTA
+
+// Many survivors (first chunk of a pool: every segment sends its K best): block b reduces survivors
+// [b kMergeCap, (b+1) kMergeCap) to their K best in parallel with the others, into `lvl`; k_merge_survivors then
+// merges ceil(c / kMergeCap) K entries instead of c.  Does nothing when the survivors fit one staged batch.
+__global__ void __launch_bounds__(256)
+k_merge_level(const double* __restrict__ surv_s, const int64_t* __restrict__ surv_i, const int* __restrict__ surv_count,
+              int K, double* __restrict__ lvl_s, int64_t* __restrict__ lvl_i) {
+  const int c = *surv_count;
+  if (c + K <= kMergeCap) return;
+  const int b0 = int(blockIdx.x) * kMergeCap;
+  if (b0 >= c) return;
+  __shared__ double ss[kMergeCap];
+  __shared__ int64_t si[kMergeCap];
+  __shared__ double ws[8];
+  __shared__ int64_t wi[8];
+  __shared__ int wp[8];
+  for (int p = threadIdx.x; p < kMergeCap; p += 256) {
+    const bool in = b0 + p < c;
+    ss[p] = in ? surv_s[b0 + p] : -INFINITY;
+    si[p] = in ? surv_i[b0 + p] : -1;
+  }
+  select_rounds<kMergeCap>(ss, si, ws, wi, wp, K, lvl_s + int64_t(blockIdx.x) * K, lvl_i + int64_t(blockIdx.x) * K);
+}
+
+// Merge the survivors of one chunk (or their per-block K best, see k_merge_level) into the running list (K entries,
+// sorted) and reset the counters.  One block.
 __global__ void __launch_bounds__(256)
 k_merge_survivors(const double* __restrict__ surv_s, const int64_t* __restrict__ surv_i, int* __restrict__ surv_count,
-                  int K, double* __restrict__ run_s, int64_t* __restrict__ run_i) {
-  constexpr int kCap = 1024;       // staged entries: 16 KB, so that the block fits beside a persistent panel CTA
+                  int K, double* __restrict__ run_s, int64_t* __restrict__ run_i, const double* __restrict__ lvl_s,
+                  const int64_t* __restrict__ lvl_i) {
+  constexpr int kCap = kMergeCap;
   __shared__ double ss[kCap];
   __shared__ int64_t si[kCap];
   __shared__ double ws[8];
   __shared__ int64_t wi[8];
   __shared__ int wp[8];
   const int tid = threadIdx.x;
-  const int c = *surv_count;
+  int c = *surv_count;
+  if (c + K > kCap) {            // k_merge_level ran: its lists are the input
+    c = (c + kCap - 1) / kCap * K;
+    surv_s = lvl_s;
+    surv_i = lvl_i;
+  }
   __syncthreads();
   if (tid == 0) {
     surv_count[0] = 0;
@@ -1204,7 +1236,10 @@ int gp_score_pool(const bbo_gp_state& s, const bbo_acq& acq, int precision, cons
       k_filter_heavy<<<unsigned(nb), 256, 0, sc>>>(qc, index_offset + c0, K, w.score, w.surv_count + 64, w.la_s,
                                                   w.la_i, w.surv_count);
       BBO_LAUNCH_CHECK();
-      k_merge_survivors<<<1, 256, 0, sc>>>(w.la_s, w.la_i, w.surv_count, K, run_s, run_i);
+      k_merge_level<<<unsigned(ceil_div(nb * int64_t(K + kFilterSlack), kMergeCap)), 256, 0, sc>>>(
+          w.la_s, w.la_i, w.surv_count, K, w.lb_s, w.lb_i);
+      BBO_LAUNCH_CHECK();
+      k_merge_survivors<<<1, 256, 0, sc>>>(w.la_s, w.la_i, w.surv_count, K, run_s, run_i, w.lb_s, w.lb_i);
       BBO_LAUNCH_CHECK();
     } else if (refine) {
       // round-based fallback (BBO_SELECT_ROUNDS=1 or a chunk too large for the survivor buffer): TF32 scores ->
@@ -1255,7 +1290,9 @@ int gp_score_pool(const bbo_gp_state& s, const bbo_acq& acq, int precision, cons
   };
   if (tf32) {
     if (q > 0) {
-      rc = score_tf32_pipeline(s, w, Xq, xq_is_f32, q, consume, st);
+      // the selection starts from an empty list unless this call continues a running list / short-list
+      const bool fresh = refine ? (refine_flags & kRefineContinue) == 0 : !keep_running;
+      rc = score_tf32_pipeline(s, w, Xq, xq_is_f32, q, consume, st, /*short_first=*/fresh);
       if (rc != BBO_OK) return rc;
     }
     if (!refine) return BBO_OK;

@@ -56,7 +56,7 @@ int topk_merge_packed(const int64_t* packed, int64_t m, int k, double* out_s, in
 using ConsumeFn = std::function<int(int64_t, int64_t, const double*, int, const double*, cudaStream_t)>;
 size_t score_tf32_extra_bytes(int64_t n, int64_t d, int64_t qp);
 int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const void* Xq, int xq_is_f32, int64_t q,
-                        const ConsumeFn& consume, cudaStream_t st);
+                        const ConsumeFn& consume, cudaStream_t st, bool short_first = false);
 int make_tf32(int64_t n, const double* linv, float* out, cudaStream_t st);
 int64_t tf32_rows(int64_t n);
 

@@ -1210,7 +1210,8 @@ constexpr int SSTAGES = 4;                         // streaming form: ring of (A
 constexpr int BSTAGES = 2, ACCS = 4;
 constexpr int EPI_WARPS = 16;
 constexpr int THREADS = 64 + 32 * EPI_WARPS;       // 576
-constexpr int OUT_BYTES = 32 * 64;                 // staging tile: 32 candidates x 32 binary16 values
+constexpr int OUT_TILE = 32 * 64;                  // staging tile: 32 candidates x 32 binary16 values
+constexpr int OUT_BYTES = 2 * OUT_TILE;            // two per epilogue warp: the TMA store of one drains under the next
 constexpr int kMaxD = 30;                          // resident-A form
 constexpr int kMaxDStream = 126;                   // streaming form (dk = 8 ceil((d+2)/8) <= 128)
 static size_t smem_bytes(int nbox) {
@@ -1436,7 +1437,7 @@ k_kstar_umma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       tc_fence_after();
       tmem_ld32_issue(tlane + uint32_t(acc * ku::BN), r);
       asm volatile("cp.async.wait_group 1;" ::: "memory");      // this block's alpha has landed
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile is free again
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the tile of two blocks ago is free
       __syncwarp();
       tmem_ld_wait(r);
       tc_fence_before();
@@ -1446,7 +1447,8 @@ k_kstar_umma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         acc_phase ^= 1;
       }
       // values -> correlations, mu partial, binary16 pairs into the 64-byte-swizzled staging tile, TMA store
-      const uint32_t sdst = stg + uint32_t(lane * 64);
+      const uint32_t stile = stg + uint32_t((blk & 1) * ku::OUT_TILE);
+      const uint32_t sdst = stile + uint32_t(lane * 64);
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8) {
         uint32_t u[4];
@@ -1476,7 +1478,7 @@ k_kstar_umma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();                          // staging tile complete; all lanes are done with al
       if (lane == 0) {
-        ku::tma_store_2d(&mapO, stg, nb * ku::BN + colq * 32, tile * ku::BM + quarter * 32);
+        ku::tma_store_2d(&mapO, stile, nb * ku::BN + colq * 32, tile * ku::BM + quarter * 32);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
       if (nb_next == 0) {
@@ -1641,7 +1643,7 @@ k_kstar_umma_stream(const __grid_constant__ CUtensorMap mapA, const __grid_const
       tc_fence_after();
       tmem_ld32_issue(tlane + uint32_t(acc * ku::BN), r);
       asm volatile("cp.async.wait_group 1;" ::: "memory");      // this block's alpha has landed
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile is free again
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the tile of two blocks ago is free
       __syncwarp();
       tmem_ld_wait(r);
       tc_fence_before();
@@ -1651,7 +1653,8 @@ k_kstar_umma_stream(const __grid_constant__ CUtensorMap mapA, const __grid_const
         acc_phase ^= 1;
       }
       // values -> correlations, mu partial, binary16 pairs into the 64-byte-swizzled staging tile, TMA store
-      const uint32_t sdst = stg + uint32_t(lane * 64);
+      const uint32_t stile = stg + uint32_t((blk & 1) * ku::OUT_TILE);
+      const uint32_t sdst = stile + uint32_t(lane * 64);
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8) {
         uint32_t u[4];
@@ -1681,7 +1684,7 @@ k_kstar_umma_stream(const __grid_constant__ CUtensorMap mapA, const __grid_const
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();                          // staging tile complete; all lanes are done with al
       if (lane == 0) {
-        ku::tma_store_2d(&mapO, stg, nb * ku::BN + colq * 32, tile * ku::BM + quarter * 32);
+        ku::tma_store_2d(&mapO, stile, nb * ku::BN + colq * 32, tile * ku::BM + quarter * 32);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
       if (nb_next == 0) {
@@ -2221,7 +2224,7 @@ static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
 // w.vpart).  K*(i+2) waits for panel(i) (Ks) and selection(i) (mu); panel(i+2) follows K*(i+2), hence also
 // selection(i) (partial sums).  `consume(c0, qc, mu, nsplit, vpart, stream)` enqueues the acquisition / top-k work.
 int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const void* Xq, int xq_is_f32, int64_t q,
-                        const ConsumeFn& consume, cudaStream_t st) {
+                        const ConsumeFn& consume, cudaStream_t st, bool short_first) {
   Tf32Aux* aux = nullptr;
   int rc = get_aux(&aux);
   if (rc != BBO_OK) return rc;
@@ -2269,7 +2272,13 @@ int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const vo
     BBO_CUDA_CHECK(cudaStreamWaitEvent(aux->sk, aux->entry, 0));
     BBO_CUDA_CHECK(cudaStreamWaitEvent(aux->ss, aux->entry, 0));
   }
-  const int64_t nchunk = ceil_div(q, w.qp);
+  // `short_first`: the selection starts from an empty list, so EVERY candidate of the first chunk passes its
+  // threshold filter and the chunk is reduced by arg-max rounds (0.5 ms for a 740 k-candidate chunk at n = 256, on
+  // the critical path of a 1.3 ms pool).  A first chunk of one wave (one 128-candidate tile per SM) establishes the
+  // threshold cheaply; from the second chunk on only a fraction of a per cent pass.
+  const int64_t wave = int64_t(sm_count()) * 128;
+  const int64_t q0 = (short_first && w.qp >= 2 * wave && q > 2 * wave && (wave / 128) % 2 == 0) ? wave : w.qp;
+  const int64_t nchunk = q <= q0 ? 1 : 1 + ceil_div(q - q0, w.qp);
   // BBO_TF32_TIMELINE=1 (debug aid): start / end of every K*, panel and selection of the call, in us after the first
   // launch, on stderr (synchronises at the end of the call)
   static const bool timeline = getenv("BBO_TF32_TIMELINE") != nullptr;
@@ -2281,8 +2290,12 @@ int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const vo
     cudaEventRecord(e, sx);
     tl.push_back(e);
   };
-  auto chunk_len = [&](int64_t i) { return (q - i * w.qp < w.qp) ? q - i * w.qp : w.qp; };
-  auto chunk_ptr = [&](int64_t i) { return static_cast<const char*>(Xq) + size_t(i) * w.qp * d * esz; };
+  auto chunk_start = [&](int64_t i) { return i == 0 ? int64_t(0) : q0 + (i - 1) * w.qp; };
+  auto chunk_len = [&](int64_t i) {
+    const int64_t full = i == 0 ? q0 : w.qp, left = q - chunk_start(i);
+    return left < full ? left : full;
+  };
+  auto chunk_ptr = [&](int64_t i) { return static_cast<const char*>(Xq) + size_t(chunk_start(i)) * d * esz; };
   {
     const int64_t qc = chunk_len(0);
     mark(aux->sk);
@@ -2328,7 +2341,7 @@ int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const vo
       BBO_CUDA_CHECK(cudaStreamWaitEvent(ssel, aux->pdone[buf], 0));
     }
     mark(ssel);
-    rc = consume(i * w.qp, qc, t.mu[i % 3], nsplit, vpart, ssel);
+    rc = consume(chunk_start(i), qc, t.mu[i % 3], nsplit, vpart, ssel);
     if (rc != BBO_OK) return rc;
     mark(ssel);
     if (two_streams) BBO_CUDA_CHECK(cudaEventRecord(aux->sdone[buf], ssel));

@@ -1,10 +1,13 @@
+"""Direct timing of CudaGP.score_pool on the headline shape (or n = argv[1]); BBO_TF32_TIMELINE=1 prints the
+per-chunk K* / panel / selection timeline of every call on stderr."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bbo_b200 as B
 from bbo_b200.benchmarks import Ackley, make_observations
 from bbo_b200.pool import uniform_pool
-D, n = 20, 4096
+D = 20
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 X, y = make_observations(Ackley(D), n, 20251019)
 cov = B.ScaleKernel(B.RBFKernel(ard_dim=D)).double()
 with torch.no_grad():
