@@ -26,6 +26,7 @@
 // SASS evidence: UTCHMMA(.2CTA) / UTMALDG / UTMASTG / LDTM / SYNCS (see profiles/).
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <algorithm>
 #include <mutex>
 #include <vector>
 
@@ -1204,21 +1205,31 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 namespace ku {
 constexpr int BM = 128, BN = 128, BOXK = 32;
 constexpr int BOX_BYTES = 128 * BOXK * 4;          // 16 KB: 128 rows x 128 bytes
-constexpr int MAXBOX = 3;                          // resident-A form: 3 dk <= 96, dk <= 32
-constexpr int MAXBOX_STREAM = 12;                  // streaming form: 3 dk <= 384, dk <= 128
-constexpr int SSTAGES = 4;                         // streaming form: ring of (A box + B box) stages
-constexpr int BSTAGES = 2, ACCS = 4;
+constexpr int MAXBOX = 8;                          // operand rows [hi | lo]: 2 dk <= 256 words, dk <= 128
+constexpr int MAXBOX_STREAM = 12;                  // (workspace sizing of Aop / Bop: rows of up to 384 words)
+constexpr int MAXRING = 6, ACCS = 4;               // B boxes in flight, TMEM accumulators
 constexpr int EPI_WARPS = 16;
 constexpr int THREADS = 64 + 32 * EPI_WARPS;       // 576
 constexpr int OUT_TILE = 32 * 64;                  // staging tile: 32 candidates x 32 binary16 values
 constexpr int OUT_BYTES = 2 * OUT_TILE;            // two per epilogue warp: the TMA store of one drains under the next
-constexpr int kMaxD = 30;                          // resident-A form
-constexpr int kMaxDStream = 126;                   // streaming form (dk = 8 ceil((d+2)/8) <= 128)
-static size_t smem_bytes(int nbox) {
-  return size_t(nbox) * BOX_BYTES * (1 + BSTAGES) + size_t(EPI_WARPS) * OUT_BYTES + 1024;
-}
-static size_t smem_bytes_stream() {
-  return size_t(SSTAGES) * 2 * BOX_BYTES + size_t(EPI_WARPS) * OUT_BYTES + 1024;
+constexpr int kMaxD = 30;                          // two A tiles resident (the next one loads under this one's MMAs)
+constexpr int kMaxDStream = 126;                   // dk = 8 ceil((d+2)/8) <= 128
+// Shared-memory plan for `nbox` boxes per operand row: A tiles (two when they fit), ring of B boxes, staging tiles
+// (two per epilogue warp when they fit).  216 KB of dynamic shared memory + 1 KB alignment slack + 7.5 KB static.
+struct Plan {
+  int na, ring, stg2;
+  size_t bytes;
+};
+static Plan plan(int nbox) {
+  const int budget = 216 * 1024;
+  Plan p;
+  p.na = (2 * nbox * BOX_BYTES + 4 * BOX_BYTES + EPI_WARPS * OUT_BYTES <= budget) ? 2 : 1;
+  p.stg2 = (p.na * nbox * BOX_BYTES + 4 * BOX_BYTES + EPI_WARPS * OUT_BYTES <= budget) ? 1 : 0;
+  const int stg = EPI_WARPS * (p.stg2 ? OUT_BYTES : OUT_TILE);
+  p.ring = (budget - p.na * nbox * BOX_BYTES - stg) / BOX_BYTES;
+  if (p.ring > MAXRING) p.ring = MAXRING;
+  p.bytes = size_t(p.na * nbox + p.ring) * BOX_BYTES + size_t(stg) + 1024;
+  return p;
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t saddr, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -1227,7 +1238,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sa
 }
 }  // namespace ku
 
-// rows of Bop: [hi | lo | hi | 0..] of the augmented observation vector (see k_prescale_aug), ktp words per row
+// rows of Bop: [hi | lo | 0..] of the augmented observation vector (see k_prescale_aug), ktp words per row
 __global__ void __launch_bounds__(256)
 k_prescale_aug_umma(const double* __restrict__ X, int64_t n, int64_t np, int d, int dk, int ktp, int matern,
                     const double* __restrict__ hyp, const double* __restrict__ alpha, uint32_t* __restrict__ Bop,
@@ -1252,13 +1263,12 @@ k_prescale_aug_umma(const double* __restrict__ X, int64_t n, int64_t np, int d, 
     split_tf32(v, hi, lo);
     row[k] = hi;
     row[dk + k] = lo;
-    row[2 * dk + k] = hi;
   }
-  for (int k = 3 * dk + lane; k < ktp; k += 32) row[k] = 0u;
+  for (int k = 2 * dk + lane; k < ktp; k += 32) row[k] = 0u;
   if (lane == 0) alpha32[j] = (j < n) ? float(alpha[j]) : 0.f;
 }
 
-// rows of Aop: [hi | hi | lo | 0..] of the augmented candidate vector (see k_prescale_cand)
+// rows of Aop: [hi | lo | 0..] of the augmented candidate vector (see k_prescale_cand)
 template <typename T1>
 __global__ void __launch_bounds__(256)
 k_prescale_cand_umma(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, int64_t qc_pad, int dk, int ktp,
@@ -1293,20 +1303,19 @@ k_prescale_cand_umma(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, int6
     uint32_t hi, lo;
     split_tf32(u, hi, lo);
     row[k] = hi;
-    row[dk + k] = hi;
-    row[2 * dk + k] = lo;
+    row[dk + k] = lo;
   }
-  for (int k = 3 * dk + lane; k < ktp; k += 32) row[k] = 0u;
+  for (int k = 2 * dk + lane; k < ktp; k += 32) row[k] = 0u;
 }
 
 template <bool MATERN>
 __global__ void __launch_bounds__(ku::THREADS, 1)
 k_kstar_umma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-             const __grid_constant__ CUtensorMap mapO, int np, int tiles, int nbox, int ksteps, int d,
-             const double* __restrict__ hyp, const float* __restrict__ alpha32, double* __restrict__ mu) {
+             const __grid_constant__ CUtensorMap mapO, int np, int tiles, int nbox, int dk, int d, int na, int ring,
+             int stg2, const double* __restrict__ hyp, const float* __restrict__ alpha32, double* __restrict__ mu) {
   using namespace tf;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t a_full, a_empty, b_full[ku::BSTAGES], b_empty[ku::BSTAGES], t_full[ku::ACCS],
+  __shared__ __align__(8) uint64_t a_full[2], a_empty[2], b_full[ku::MAXRING], b_empty[ku::MAXRING], t_full[ku::ACCS],
       t_empty[ku::ACCS];
   __shared__ uint32_t tmem_base_sh;
   __shared__ float mu_sh[2][3][ku::BM];
@@ -1314,13 +1323,17 @@ k_kstar_umma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  const int op_bytes = nbox * ku::BOX_BYTES;       // one operand tile (A, or one B stage)
+  const int a_bytes = nbox * ku::BOX_BYTES;        // one candidate tile: 128 rows x nbox boxes
+  const int ring_off = na * a_bytes;               // B boxes follow the A tiles
+  const int stg_off = ring_off + ring * ku::BOX_BYTES;
   const int nblk = np / ku::BN;
 
   if (threadIdx.x == 0) {
-    mbar_init(&a_full, 1);
-    mbar_init(&a_empty, 1);
-    for (int s = 0; s < ku::BSTAGES; ++s) {
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&a_full[a], 1);
+      mbar_init(&a_empty[a], 1);
+    }
+    for (int s = 0; s < ku::MAXRING; ++s) {
       mbar_init(&b_full[s], 1);
       mbar_init(&b_empty[s], 1);
     }
@@ -1343,256 +1356,77 @@ k_kstar_umma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 
   if (warp == 0) {
     if (lane == 0) {   // ===== TMA producer =====
-      uint32_t a_phase = 0, phase = 0;
-      int stage = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        mbar_wait(&a_empty, a_phase ^ 1);            // every MMA of the previous tile has read A
-        mbar_expect_tx(&a_full, uint32_t(op_bytes));
+      uint32_t a_phase[2] = {0, 0}, phase = 0;
+      int stage = 0, abuf = 0;
+      auto load_a = [&](int tile, int buf) {
+        mbar_wait(&a_empty[buf], a_phase[buf] ^ 1);   // every MMA that read this buffer has completed
+        a_phase[buf] ^= 1;
+        mbar_expect_tx(&a_full[buf], uint32_t(a_bytes));
         for (int b = 0; b < nbox; ++b)
-          tma_load_2d(sgen + b * ku::BOX_BYTES, &mapA, &a_full, b * ku::BOXK, tile * ku::BM);
-        a_phase ^= 1;
+          tma_load_2d(sgen + buf * a_bytes + b * ku::BOX_BYTES, &mapA, &a_full[buf], b * ku::BOXK, tile * ku::BM);
+      };
+      if (int(blockIdx.x) < tiles) load_a(blockIdx.x, 0);
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int next = tile + int(gridDim.x);
         for (int nb = 0; nb < nblk; ++nb) {
-          mbar_wait(&b_empty[stage], phase ^ 1);
-          uint8_t* sb = sgen + (1 + stage) * op_bytes;
-          mbar_expect_tx(&b_full[stage], uint32_t(op_bytes));
-          for (int b = 0; b < nbox; ++b)
-            tma_load_2d(sb + b * ku::BOX_BYTES, &mapB, &b_full[stage], b * ku::BOXK, nb * ku::BN);
-          if (++stage == ku::BSTAGES) {
-            stage = 0;
-            phase ^= 1;
+          // two A tiles: the next one is requested one block before this tile ends (its buffer was released when
+          // the previous tile's MMAs completed, long ago)
+          if (na == 2 && nb == nblk - 1 && next < tiles) load_a(next, abuf ^ 1);
+          for (int b = 0; b < nbox; ++b) {
+            mbar_wait(&b_empty[stage], phase ^ 1);
+            mbar_expect_tx(&b_full[stage], uint32_t(ku::BOX_BYTES));
+            tma_load_2d(sgen + ring_off + stage * ku::BOX_BYTES, &mapB, &b_full[stage], b * ku::BOXK, nb * ku::BN);
+            if (++stage == ring) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
         }
+        if (na == 2) abuf ^= 1;
+        else if (next < tiles) load_a(next, 0);       // one A tile: reloaded when this tile's MMAs are done
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {   // ===== MMA issuer =====
-      // D=f32, A=B=tf32, both K-major, N=128, M=128
+      // D=f32, A=B=tf32, both K-major, N=128, M=128.  Operand rows are [hi | lo] (2 dk words): a box of the B row
+      // holds up to four 8-word k-steps; a `hi` step meets the candidate's hi AND lo step, a `lo` step its hi step
+      // (hi hi + lo hi + hi lo: the 3xTF32 product), so every B box crosses L2 -> SM once per 128 x 128 block and the
+      // candidate tile not at all.
       const uint32_t idesc =
           (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(ku::BN >> 3) << 17) | (uint32_t(ku::BM >> 4) << 24);
-      uint32_t a_phase = 0, phase = 0, acc_phase = 0;
-      int stage = 0, acc = 0;
+      uint32_t a_phase[2] = {0, 0}, phase = 0, acc_phase = 0;
+      int stage = 0, acc = 0, abuf = 0;
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        mbar_wait(&a_full, a_phase);
-        a_phase ^= 1;
+        mbar_wait(&a_full[abuf], a_phase[abuf]);
+        a_phase[abuf] ^= 1;
+        const uint32_t sa = sbase + uint32_t(abuf * a_bytes);
+        auto adesc = [&](int w) -> uint64_t {   // k-step starting at word w of the candidate rows
+          return make_desc(sa + uint32_t((w >> 5) * ku::BOX_BYTES)) + uint64_t((w & 31) >> 2);
+        };
         for (int nb = 0; nb < nblk; ++nb) {
           mbar_wait(&t_empty[acc], acc_phase ^ 1);
-          mbar_wait(&b_full[stage], phase);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + uint32_t(acc * ku::BN);
-          const uint32_t sb = sbase + uint32_t((1 + stage) * op_bytes);
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint32_t off = uint32_t((ks >> 2) * ku::BOX_BYTES);
-            const uint64_t adv = uint64_t((ks & 3) * 2);   // 32 bytes inside the 128-byte swizzle atom
-            tc_mma_tf32(d_tmem, make_desc(sbase + off) + adv, make_desc(sb + off) + adv, idesc, ks != 0 ? 1u : 0u);
-          }
-          tc_commit(&b_empty[stage]);
-          tc_commit(&t_full[acc]);
-          if (++stage == ku::BSTAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
-          if (++acc == ku::ACCS) {
-            acc = 0;
-            acc_phase ^= 1;
-          }
-        }
-        tc_commit(&a_empty);
-      }
-    }
-  } else {   // ===== epilogue (warps 2..17) =====
-    // warp = (TMEM lane quarter, 32-column slab): 16 warps, four per scheduler, so that one warp's TMEM load, MUFU
-    // and TMA-store latencies are covered by the other three
-    const int ew = warp - 2, quarter = warp & 3, colq = ew >> 2;
-    const int row = quarter * 32 + lane;
-    const uint32_t stg = sbase + uint32_t(3 * op_bytes + ew * ku::OUT_BYTES);
-    const float s2 = float(hyp[2 * d]);
-    const float kLog2e = 1.4426950408889634f;
-    const double cmean = hyp[2 * d + 1];
-    const uint32_t tlane = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(colq * 32);
-    const float* abase = alpha32 + colq * 32;
-    float m = 0.f;
-    // alpha of this warp's 32 columns, one block ahead (cp.async, per-warp double buffer): the values are used
-    // once per tile, so they always come from L2
-    float* alw = &al_sh[ew][0][0];
-    auto alpha_fetch = [&](int nb_, int buf_) {
-      if (lane < 8) {
-        const unsigned sa = smem_u32(alw + buf_ * 32 + lane * 4);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(abase + nb_ * ku::BN + lane * 4)
-                     : "memory");
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    const int my_tiles = (tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
-    const int nblocks = my_tiles * nblk;     // 128 x 128 blocks this CTA produces, accumulators in ring order
-    uint32_t acc_phase = 0;
-    int acc = 0;
-    if (nblocks > 0) alpha_fetch(0, 0);
-    int tile = blockIdx.x, nb = 0, tcount = 0;
-    for (int blk = 0; blk < nblocks; ++blk) {
-      const int nb_next = (nb + 1 == nblk) ? 0 : nb + 1;
-      const float* al = alw + (blk & 1) * 32;
-      alpha_fetch(nb_next, (blk + 1) & 1);                       // next block's alpha (harmless after the last)
-      uint32_t r[32];
-      mbar_wait(&t_full[acc], acc_phase);
-      tc_fence_after();
-      tmem_ld32_issue(tlane + uint32_t(acc * ku::BN), r);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");      // this block's alpha has landed
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the tile of two blocks ago is free
-      __syncwarp();
-      tmem_ld_wait(r);
-      tc_fence_before();
-      mbar_arrive(&t_empty[acc]);
-      if (++acc == ku::ACCS) {
-        acc = 0;
-        acc_phase ^= 1;
-      }
-      // values -> correlations, mu partial, binary16 pairs into the 64-byte-swizzled staging tile, TMA store
-      const uint32_t stile = stg + uint32_t((blk & 1) * ku::OUT_TILE);
-      const uint32_t sdst = stile + uint32_t(lane * 64);
-#pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {
-        uint32_t u[4];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float4 av = *reinterpret_cast<const float4*>(al + c8 * 8 + h * 4);
-          const float a4[4] = {av.x, av.y, av.z, av.w};
-          float cv[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float x = __uint_as_float(r[c8 * 8 + h * 4 + e]);
-            if (!MATERN) {
-              cv[e] = ex2_approx(fminf(x, 0.f));
-            } else {
-              const float rr = 2.2360679775f * sqrtf(fmaxf(x, 0.f));
-              cv[e] = fmaf(rr, fmaf(rr, 1.f / 3.f, 1.f), 1.f) * ex2_approx(-kLog2e * rr);
-            }
-            m = fmaf(cv[e], a4[e], m);
-          }
-          u[2 * h] = pack_half2(cv[0], cv[1]);
-          u[2 * h + 1] = pack_half2(cv[2], cv[3]);
-        }
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdst + uint32_t((c8 ^ ((lane >> 1) & 3)) * 16)),
-                     "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3])
-                     : "memory");
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();                          // staging tile complete; all lanes are done with al
-      if (lane == 0) {
-        ku::tma_store_2d(&mapO, stile, nb * ku::BN + colq * 32, tile * ku::BM + quarter * 32);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
-      if (nb_next == 0) {
-        // mu = c + the four column slabs in a fixed order
-        if (colq > 0) mu_sh[tcount & 1][colq - 1][row] = m;
-        asm volatile("bar.sync 1, %0;" ::"n"(ku::EPI_WARPS * 32) : "memory");
-        if (colq == 0)
-          mu[int64_t(tile) * ku::BM + row] =
-              cmean + double(s2) * double(((m + mu_sh[tcount & 1][0][row]) + mu_sh[tcount & 1][1][row]) +
-                                          mu_sh[tcount & 1][2][row]);
-        m = 0.f;
-        tile += gridDim.x;
-        ++tcount;
-      }
-      nb = nb_next;
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
-  }
-}
-
-// Streaming form of k_kstar_umma for 30 < d <= 126 (BASELINE configs 3 and 5: d = 50, 100): with 3 dk up to 384
-// words the candidate tile (up to 192 KB) no longer fits beside the observation ring, so BOTH operands are streamed
-// in 32-word boxes through a ring of ku::SSTAGES (A box + B box) stages; accumulator ring, epilogue and TMA store are
-// those of k_kstar_umma.  L2 -> SM traffic: 2 x nbox x 16 KB per 128 x 128 block.
-template <bool MATERN>
-__global__ void __launch_bounds__(ku::THREADS, 1)
-k_kstar_umma_stream(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-             const __grid_constant__ CUtensorMap mapO, int np, int tiles, int nbox, int ksteps, int d,
-             const double* __restrict__ hyp, const float* __restrict__ alpha32, double* __restrict__ mu) {
-  using namespace tf;
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t s_full[ku::SSTAGES], s_empty[ku::SSTAGES], t_full[ku::ACCS], t_empty[ku::ACCS];
-  __shared__ uint32_t tmem_base_sh;
-  __shared__ float mu_sh[2][3][ku::BM];
-  __shared__ __align__(16) float al_sh[ku::EPI_WARPS][2][32];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  constexpr int stage_bytes = 2 * ku::BOX_BYTES;   // one ring stage: a 128 x 32-word box of each operand
-  const int nblk = np / ku::BN;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < ku::SSTAGES; ++s) {
-      mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], 1);
-    }
-    for (int a = 0; a < ku::ACCS; ++a) {
-      mbar_init(&t_full[a], 1);
-      mbar_init(&t_empty[a], ku::EPI_WARPS * 32);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
-                 "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_sh;
-
-  if (warp == 0) {
-    if (lane == 0) {   // ===== TMA producer =====
-      uint32_t phase = 0;
-      int stage = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        for (int nb = 0; nb < nblk; ++nb) {
-          for (int b = 0; b < nbox; ++b) {           // box b of BOTH operands: the candidate tile does not stay resident
-            mbar_wait(&s_empty[stage], phase ^ 1);
-            uint8_t* sa = sgen + stage * stage_bytes;
-            mbar_expect_tx(&s_full[stage], uint32_t(stage_bytes));
-            tma_load_2d(sa, &mapA, &s_full[stage], b * ku::BOXK, tile * ku::BM);
-            tma_load_2d(sa + ku::BOX_BYTES, &mapB, &s_full[stage], b * ku::BOXK, nb * ku::BN);
-            if (++stage == ku::SSTAGES) {
-              stage = 0;
-              phase ^= 1;
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {   // ===== MMA issuer =====
-      // D=f32, A=B=tf32, both K-major, N=128, M=128
-      const uint32_t idesc =
-          (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(ku::BN >> 3) << 17) | (uint32_t(ku::BM >> 4) << 24);
-      uint32_t phase = 0, acc_phase = 0;
-      int stage = 0, acc = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        for (int nb = 0; nb < nblk; ++nb) {
-          mbar_wait(&t_empty[acc], acc_phase ^ 1);
-          const uint32_t d_tmem = tmem_base + uint32_t(acc * ku::BN);
+          uint32_t started = 0;
           for (int b = 0; b < nbox; ++b) {
-            mbar_wait(&s_full[stage], phase);
+            mbar_wait(&b_full[stage], phase);
             tc_fence_after();
-            const uint32_t sa = sbase + uint32_t(stage * stage_bytes);
-            const int nks = ksteps - 4 * b < 4 ? ksteps - 4 * b : 4;     // K = 8 steps inside this 32-word box
-            for (int ks = 0; ks < nks; ++ks) {
-              const uint64_t adv = uint64_t(ks * 2);   // 32 bytes inside the 128-byte swizzle atom
-              tc_mma_tf32(d_tmem, make_desc(sa) + adv, make_desc(sa + ku::BOX_BYTES) + adv, idesc,
-                          (b | ks) != 0 ? 1u : 0u);
+            const uint64_t bbase = make_desc(sbase + uint32_t(ring_off + stage * ku::BOX_BYTES));
+            for (int s4 = 0; s4 < 4; ++s4) {
+              const int w = 32 * b + 8 * s4;
+              if (w >= 2 * dk) break;
+              const uint64_t bdesc = bbase + uint64_t(s4 * 2);
+              if (w < dk) {
+                tc_mma_tf32(d_tmem, adesc(w), bdesc, idesc, started);
+                started = 1;
+                tc_mma_tf32(d_tmem, adesc(dk + w), bdesc, idesc, 1u);
+              } else {
+                tc_mma_tf32(d_tmem, adesc(w - dk), bdesc, idesc, started);
+                started = 1;
+              }
             }
-            tc_commit(&s_empty[stage]);
-            if (++stage == ku::SSTAGES) {
+            tc_commit(&b_empty[stage]);
+            if (++stage == ring) {
               stage = 0;
               phase ^= 1;
             }
@@ -1603,6 +1437,8 @@ k_kstar_umma_stream(const __grid_constant__ CUtensorMap mapA, const __grid_const
             acc_phase ^= 1;
           }
         }
+        tc_commit(&a_empty[abuf]);
+        if (na == 2) abuf ^= 1;
       }
     }
   } else {   // ===== epilogue (warps 2..17) =====
@@ -1610,7 +1446,7 @@ k_kstar_umma_stream(const __grid_constant__ CUtensorMap mapA, const __grid_const
     // and TMA-store latencies are covered by the other three
     const int ew = warp - 2, quarter = warp & 3, colq = ew >> 2;
     const int row = quarter * 32 + lane;
-    const uint32_t stg = sbase + uint32_t(ku::SSTAGES * stage_bytes + ew * ku::OUT_BYTES);
+    const uint32_t stg = sbase + uint32_t(stg_off + ew * (stg2 ? ku::OUT_BYTES : ku::OUT_TILE));
     const float s2 = float(hyp[2 * d]);
     const float kLog2e = 1.4426950408889634f;
     const double cmean = hyp[2 * d + 1];
@@ -1643,7 +1479,10 @@ k_kstar_umma_stream(const __grid_constant__ CUtensorMap mapA, const __grid_const
       tc_fence_after();
       tmem_ld32_issue(tlane + uint32_t(acc * ku::BN), r);
       asm volatile("cp.async.wait_group 1;" ::: "memory");      // this block's alpha has landed
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the tile of two blocks ago is free
+      if (lane == 0) {   // the staging tile about to be written is free again
+        if (stg2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
       __syncwarp();
       tmem_ld_wait(r);
       tc_fence_before();
@@ -1653,7 +1492,7 @@ k_kstar_umma_stream(const __grid_constant__ CUtensorMap mapA, const __grid_const
         acc_phase ^= 1;
       }
       // values -> correlations, mu partial, binary16 pairs into the 64-byte-swizzled staging tile, TMA store
-      const uint32_t stile = stg + uint32_t((blk & 1) * ku::OUT_TILE);
+      const uint32_t stile = stg + uint32_t(stg2 ? (blk & 1) * ku::OUT_TILE : 0);
       const uint32_t sdst = stile + uint32_t(lane * 64);
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8) {
@@ -1964,7 +1803,7 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
   const int64_t np = w.np;
   prof_begin(kProfKstar, st);
   if (use_kstar_umma(s.h.d)) {
-    const int dk = 8 * ((s.h.d + 2 + 7) / 8), ktp = 32 * ((3 * dk + 31) / 32), nbox = ktp / 32;
+    const int dk = 8 * ((s.h.d + 2 + 7) / 8), ktp = 32 * ((2 * dk + 31) / 32), nbox = ktp / 32;
     const bool matern = s.h.kind == BBO_KERNEL_MATERN52;
     if (xq_is_f32)
       k_prescale_cand_umma<float><<<unsigned(qc_pad / 8), 256, 0, st>>>(s.h, static_cast<const float*>(Xq), qc, qc_pad,
@@ -1975,10 +1814,10 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
     BBO_LAUNCH_CHECK();
     static DeviceOnce attr_once;
     if (attr_once.first()) {
-      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          int(ku::smem_bytes(ku::MAXBOX))));
-      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          int(ku::smem_bytes(ku::MAXBOX))));
+      size_t most = 0;
+      for (int b = 1; b <= ku::MAXBOX; ++b) most = std::max(most, ku::plan(b).bytes);
+      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(most)));
+      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(most)));
     }
     CUtensorMap mapA, mapB, mapO;
     int rc = make_map(&mapA, reinterpret_cast<const float*>(t.Aop), qc_pad, ktp, ku::BM, ku::BOXK);
@@ -1990,30 +1829,15 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
     const int tiles = int(qc_pad / ku::BM);
     const int grid = tiles < sm_count() ? tiles : sm_count();
     const double* hyp = s.hyp;
-    if (nbox > ku::MAXBOX) {   // streaming form: both operands in boxes through one ring
-      static DeviceOnce stream_attr_once;
-      if (stream_attr_once.first()) {
-        BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_umma_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            int(ku::smem_bytes_stream())));
-        BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_umma_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            int(ku::smem_bytes_stream())));
-      }
-      const size_t sm = ku::smem_bytes_stream();
-      if (matern)
-        k_kstar_umma_stream<true><<<unsigned(grid), ku::THREADS, sm, st>>>(mapA, mapB, mapO, int(np), tiles, nbox,
-                                                                          3 * dk / 8, s.h.d, hyp, t.alpha32, mu_chunk);
-      else
-        k_kstar_umma_stream<false><<<unsigned(grid), ku::THREADS, sm, st>>>(mapA, mapB, mapO, int(np), tiles, nbox,
-                                                                           3 * dk / 8, s.h.d, hyp, t.alpha32, mu_chunk);
-    } else {
-      const size_t sm = ku::smem_bytes(nbox);
-      if (matern)
-        k_kstar_umma<true><<<unsigned(grid), ku::THREADS, sm, st>>>(mapA, mapB, mapO, int(np), tiles, nbox, 3 * dk / 8,
-                                                                   s.h.d, hyp, t.alpha32, mu_chunk);
-      else
-        k_kstar_umma<false><<<unsigned(grid), ku::THREADS, sm, st>>>(mapA, mapB, mapO, int(np), tiles, nbox, 3 * dk / 8,
-                                                                    s.h.d, hyp, t.alpha32, mu_chunk);
-    }
+    const ku::Plan pl = ku::plan(nbox);
+    if (pl.ring < 2 || nbox > ku::MAXBOX) return BBO_ERR_BAD_SHAPE;
+    if (matern)
+      k_kstar_umma<true><<<unsigned(grid), ku::THREADS, pl.bytes, st>>>(mapA, mapB, mapO, int(np), tiles, nbox, dk, s.h.d,
+                                                                       pl.na, pl.ring, pl.stg2, hyp, t.alpha32, mu_chunk);
+    else
+      k_kstar_umma<false><<<unsigned(grid), ku::THREADS, pl.bytes, st>>>(mapA, mapB, mapO, int(np), tiles, nbox, dk,
+                                                                        s.h.d, pl.na, pl.ring, pl.stg2, hyp, t.alpha32,
+                                                                        mu_chunk);
   } else if (s.h.d <= kMma2MaxD) {
     const int ks = (s.h.d + 2 + 7) / 8;
     const unsigned grid = unsigned(qc_pad / 128);
@@ -2248,7 +2072,7 @@ int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const vo
   const size_t esz = xq_is_f32 ? sizeof(float) : sizeof(double);
   const int d = s.h.d;
   if (use_kstar_umma(d)) {
-    const int dk = 8 * ((d + 2 + 7) / 8), ktp = 32 * ((3 * dk + 31) / 32);
+    const int dk = 8 * ((d + 2 + 7) / 8), ktp = 32 * ((2 * dk + 31) / 32);
     k_prescale_aug_umma<<<unsigned(ceil_div(w.np, 8)), 256, 0, st>>>(s.X, s.n, w.np, d, dk, ktp,
                                                                     s.h.kind == BBO_KERNEL_MATERN52 ? 1 : 0, s.hyp,
                                                                     s.alpha, t.Bop, t.alpha32);

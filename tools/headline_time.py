@@ -6,7 +6,7 @@ import numpy as np, torch
 import bbo_b200 as B
 from bbo_b200.benchmarks import Ackley, make_observations
 from bbo_b200.pool import uniform_pool
-D = 20
+D = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 X, y = make_observations(Ackley(D), n, 20251019)
 cov = B.ScaleKernel(B.RBFKernel(ard_dim=D)).double()
@@ -15,7 +15,8 @@ with torch.no_grad():
     cov.variance.fill_(float(np.log(np.expm1(1.0))))
 gp = B.CudaGP(torch.as_tensor(X), torch.as_tensor(y).reshape(-1, 1), B.ConstantMean().double(), cov, noise_variance=1e-4)
 acq = B.EI(float(y.max()))
-pool = uniform_pool(3, 0, 1 << 20, D)
+pool = uniform_pool(3, 0, (1 << 20) if n <= 4096 else (1 << 19), D)
+Q = pool.shape[0]
 for prec in ("tf32+refine", "tf32"):
     for _ in range(3):
         gp.score_pool(pool, acq, 8, precision=prec)
@@ -28,4 +29,4 @@ for prec in ("tf32+refine", "tf32"):
         b.record()
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / 5
-        print(prec, "ms/step", ms, "Mcand/s", (1 << 20) / ms / 1e3, flush=True)
+        print(prec, "ms/step", ms, "Mcand/s", Q / ms / 1e3, flush=True)
