@@ -1231,6 +1231,11 @@ static Plan plan(int nbox) {
   p.bytes = size_t(p.na * nbox + p.ring) * BOX_BYTES + size_t(stg) + 1024;
   return p;
 }
+// descriptor offset of the k-step that starts at word w of an operand row stored in 32-word boxes (128-byte swizzle):
+// box w / 32 (BOX_BYTES >> 4 per box in the 16-byte address field), 32 bytes per k-step inside the swizzle atom
+__host__ __device__ constexpr uint64_t desc_off(int w) {
+  return uint64_t((w >> 5) * (BOX_BYTES >> 4) + ((w & 31) >> 2));
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t saddr, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(map), "r"(saddr), "r"(c0), "r"(c1)
@@ -1308,7 +1313,7 @@ k_prescale_cand_umma(bbo_gp_hyper h, const T1* __restrict__ Xq, int64_t qc, int6
   for (int k = 2 * dk + lane; k < ktp; k += 32) row[k] = 0u;
 }
 
-template <bool MATERN>
+template <bool MATERN, int DKS>     // DKS = dk / 8 k-steps per half row
 __global__ void __launch_bounds__(ku::THREADS, 1)
 k_kstar_umma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
              const __grid_constant__ CUtensorMap mapO, int np, int tiles, int nbox, int dk, int d, int na, int ring,
@@ -1356,11 +1361,12 @@ k_kstar_umma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 
   if (warp == 0) {
     if (lane == 0) {   // ===== TMA producer =====
-      uint32_t a_phase[2] = {0, 0}, phase = 0;
+      uint32_t a_phase0 = 0, a_phase1 = 0, phase = 0;
       int stage = 0, abuf = 0;
       auto load_a = [&](int tile, int buf) {
-        mbar_wait(&a_empty[buf], a_phase[buf] ^ 1);   // every MMA that read this buffer has completed
-        a_phase[buf] ^= 1;
+        uint32_t& ph = buf == 0 ? a_phase0 : a_phase1;
+        mbar_wait(&a_empty[buf], ph ^ 1);   // every MMA that read this buffer has completed
+        ph ^= 1;
         mbar_expect_tx(&a_full[buf], uint32_t(a_bytes));
         for (int b = 0; b < nbox; ++b)
           tma_load_2d(sgen + buf * a_bytes + b * ku::BOX_BYTES, &mapA, &a_full[buf], b * ku::BOXK, tile * ku::BM);
@@ -1391,38 +1397,44 @@ k_kstar_umma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       // D=f32, A=B=tf32, both K-major, N=128, M=128.  Operand rows are [hi | lo] (2 dk words): a box of the B row
       // holds up to four 8-word k-steps; a `hi` step meets the candidate's hi AND lo step, a `lo` step its hi step
       // (hi hi + lo hi + hi lo: the 3xTF32 product), so every B box crosses L2 -> SM once per 128 x 128 block and the
-      // candidate tile not at all.
+      // candidate tile not at all.  This one thread feeds the tensor core of the SM: with run-time loop bounds it
+      // spent ~300 instructions of descriptor arithmetic per 9-MMA block and the epilogue warps waited for it (ncu:
+      // 29 % of all stall samples on their accumulator wait); DKS = dk / 8 is a template parameter so that every
+      // descriptor is the tile's / the stage's base plus a compile-time constant.
+      constexpr int DK = 8 * DKS, NBOX = (2 * DK + 31) / 32;
       const uint32_t idesc =
           (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(ku::BN >> 3) << 17) | (uint32_t(ku::BM >> 4) << 24);
-      uint32_t a_phase[2] = {0, 0}, phase = 0, acc_phase = 0;
+      uint32_t a_phase0 = 0, a_phase1 = 0, phase = 0, acc_phase = 0;
       int stage = 0, acc = 0, abuf = 0;
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        mbar_wait(&a_full[abuf], a_phase[abuf]);
-        a_phase[abuf] ^= 1;
-        const uint32_t sa = sbase + uint32_t(abuf * a_bytes);
-        auto adesc = [&](int w) -> uint64_t {   // k-step starting at word w of the candidate rows
-          return make_desc(sa + uint32_t((w >> 5) * ku::BOX_BYTES)) + uint64_t((w & 31) >> 2);
-        };
+        if (abuf == 0) {
+          mbar_wait(&a_full[0], a_phase0);
+          a_phase0 ^= 1;
+        } else {
+          mbar_wait(&a_full[1], a_phase1);
+          a_phase1 ^= 1;
+        }
+        const uint64_t a0 = make_desc(sbase + uint32_t(abuf * a_bytes));
         for (int nb = 0; nb < nblk; ++nb) {
           mbar_wait(&t_empty[acc], acc_phase ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + uint32_t(acc * ku::BN);
-          uint32_t started = 0;
-          for (int b = 0; b < nbox; ++b) {
+#pragma unroll
+          for (int b = 0; b < NBOX; ++b) {
             mbar_wait(&b_full[stage], phase);
             tc_fence_after();
             const uint64_t bbase = make_desc(sbase + uint32_t(ring_off + stage * ku::BOX_BYTES));
+#pragma unroll
             for (int s4 = 0; s4 < 4; ++s4) {
-              const int w = 32 * b + 8 * s4;
-              if (w >= 2 * dk) break;
-              const uint64_t bdesc = bbase + uint64_t(s4 * 2);
-              if (w < dk) {
-                tc_mma_tf32(d_tmem, adesc(w), bdesc, idesc, started);
-                started = 1;
-                tc_mma_tf32(d_tmem, adesc(dk + w), bdesc, idesc, 1u);
-              } else {
-                tc_mma_tf32(d_tmem, adesc(w - dk), bdesc, idesc, started);
-                started = 1;
+              const int w = 32 * b + 8 * s4;          // compile-time after unrolling
+              if (w < 2 * DK) {
+                const uint64_t bdesc = bbase + uint64_t(s4 * 2);
+                if (w < DK) {
+                  tc_mma_tf32(d_tmem, a0 + ku::desc_off(w), bdesc, idesc, w != 0 ? 1u : 0u);
+                  tc_mma_tf32(d_tmem, a0 + ku::desc_off(DK + w), bdesc, idesc, 1u);
+                } else {
+                  tc_mma_tf32(d_tmem, a0 + ku::desc_off(w - DK), bdesc, idesc, 1u);
+                }
               }
             }
             tc_commit(&b_empty[stage]);
@@ -1812,13 +1824,6 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
       k_prescale_cand_umma<double><<<unsigned(qc_pad / 8), 256, 0, st>>>(s.h, static_cast<const double*>(Xq), qc,
                                                                         qc_pad, dk, ktp, s.hyp, t.Aop);
     BBO_LAUNCH_CHECK();
-    static DeviceOnce attr_once;
-    if (attr_once.first()) {
-      size_t most = 0;
-      for (int b = 1; b <= ku::MAXBOX; ++b) most = std::max(most, ku::plan(b).bytes);
-      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(most)));
-      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(most)));
-    }
     CUtensorMap mapA, mapB, mapO;
     int rc = make_map(&mapA, reinterpret_cast<const float*>(t.Aop), qc_pad, ktp, ku::BM, ku::BOXK);
     if (rc != BBO_OK) return rc;
@@ -1829,15 +1834,50 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
     const int tiles = int(qc_pad / ku::BM);
     const int grid = tiles < sm_count() ? tiles : sm_count();
     const double* hyp = s.hyp;
-    const ku::Plan pl = ku::plan(nbox);
+    ku::Plan pl = ku::plan(nbox);
+    if (const char* e = getenv("BBO_KSTAR_NA")) pl.na = atoi(e);         // tuning aids (the plan stays within the budget
+    if (const char* e = getenv("BBO_KSTAR_RING")) pl.ring = atoi(e);     // only for values not above the planned ones)
+    if (const char* e = getenv("BBO_KSTAR_STG2")) pl.stg2 = atoi(e);
     if (pl.ring < 2 || nbox > ku::MAXBOX) return BBO_ERR_BAD_SHAPE;
-    if (matern)
-      k_kstar_umma<true><<<unsigned(grid), ku::THREADS, pl.bytes, st>>>(mapA, mapB, mapO, int(np), tiles, nbox, dk, s.h.d,
-                                                                       pl.na, pl.ring, pl.stg2, hyp, t.alpha32, mu_chunk);
-    else
-      k_kstar_umma<false><<<unsigned(grid), ku::THREADS, pl.bytes, st>>>(mapA, mapB, mapO, int(np), tiles, nbox, dk,
-                                                                        s.h.d, pl.na, pl.ring, pl.stg2, hyp, t.alpha32,
-                                                                        mu_chunk);
+    size_t most = 0;
+    for (int b = 1; b <= ku::MAXBOX; ++b) most = std::max(most, ku::plan(b).bytes);
+#define BBO_KSTAR_UMMA(DKS_)                                                                                        \
+  case DKS_: {                                                                                                      \
+    static DeviceOnce once;                                                                                         \
+    if (once.first()) {                                                                                             \
+      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_umma<false, DKS_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                          int(most)));                                                              \
+      BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_umma<true, DKS_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                          int(most)));                                                              \
+    }                                                                                                               \
+    if (matern)                                                                                                     \
+      k_kstar_umma<true, DKS_><<<unsigned(grid), ku::THREADS, pl.bytes, st>>>(                                      \
+          mapA, mapB, mapO, int(np), tiles, nbox, dk, s.h.d, pl.na, pl.ring, pl.stg2, hyp, t.alpha32, mu_chunk);    \
+    else                                                                                                            \
+      k_kstar_umma<false, DKS_><<<unsigned(grid), ku::THREADS, pl.bytes, st>>>(                                     \
+          mapA, mapB, mapO, int(np), tiles, nbox, dk, s.h.d, pl.na, pl.ring, pl.stg2, hyp, t.alpha32, mu_chunk);    \
+  } break;
+    switch (dk / 8) {
+      BBO_KSTAR_UMMA(1)
+      BBO_KSTAR_UMMA(2)
+      BBO_KSTAR_UMMA(3)
+      BBO_KSTAR_UMMA(4)
+      BBO_KSTAR_UMMA(5)
+      BBO_KSTAR_UMMA(6)
+      BBO_KSTAR_UMMA(7)
+      BBO_KSTAR_UMMA(8)
+      BBO_KSTAR_UMMA(9)
+      BBO_KSTAR_UMMA(10)
+      BBO_KSTAR_UMMA(11)
+      BBO_KSTAR_UMMA(12)
+      BBO_KSTAR_UMMA(13)
+      BBO_KSTAR_UMMA(14)
+      BBO_KSTAR_UMMA(15)
+      BBO_KSTAR_UMMA(16)
+      default:
+        return BBO_ERR_BAD_ARG;
+    }
+#undef BBO_KSTAR_UMMA
   } else if (s.h.d <= kMma2MaxD) {
     const int ks = (s.h.d + 2 + 7) / 8;
     const unsigned grid = unsigned(qc_pad / 128);
