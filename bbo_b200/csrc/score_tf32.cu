@@ -453,6 +453,42 @@ __device__ __forceinline__ void mma_f16_2sm(uint32_t d_tmem, uint64_t adesc, uin
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(p));
+  return p != 0;
+}
+// the same as tf::mbar_wait / commit_2sm with the barrier's shared address computed by the caller (once, outside its
+// loop: the conversion of a __shared__ pointer costs three uniform-datapath instructions every time)
+__device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity) {
+  uint32_t ok = 0;
+  uint64_t t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((spin & 1023u) == 1023u) {   // time-based bound: 2 s without progress -> trap
+      uint64_t t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 2000000000ull) asm volatile("trap;");
+    }
+  }
+}
+__device__ __forceinline__ void commit_2sm_addr(uint32_t addr) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(addr), "h"(uint16_t(3))
+               : "memory");
+}
 __device__ __forceinline__ void commit_2sm(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(tf::smem_u32(bar)), "h"(uint16_t(3))
@@ -520,95 +556,131 @@ k_vnorm_tf32_2sm(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   const uint32_t tmem_base = tmem_base_sh;
 
   if (warp == 0) {
-    if (lane == 0) {   // ===== TMA producer (both CTAs) =====
+    {   // ===== TMA producer (both CTAs): the whole warp walks the loop, an elect.sync lane issues =====
+      const bool el = tf2::elect_one();
+      const uint32_t empty0 = smem_u32(&empty_bar[0]);
+      const uint32_t lfull0 = tf2::map_to_cta(smem_u32(&full_bar[0]), 0);   // the LEADER's full barriers
+      const int half = int(cta_rank) * (tf2::BN / 2);
       int stage = 0;
       uint32_t phase = 0;
+      uint8_t* sa = sgen;
+      // one stage: K* tile of this CTA's candidates + this CTA's half (128 rows, starting at r0 / r1) of the L^-1
+      // tiles of the active row blocks
+      auto do_stage = [&](int k, int c0, bool act0, bool act1, int r0, int r1) {
+        tf2::mbar_wait_addr(empty0 + uint32_t(stage) * 8u, phase ^ 1);
+        if (el) {
+          const uint32_t lbar = lfull0 + uint32_t(stage) * 8u;
+          tf2::mbar_expect_tx_cluster(lbar, tf2::A_BYTES + (act0 ? tf2::BH_BYTES : 0) + (act1 ? tf2::BH_BYTES : 0));
+          tf2::tma_load_2d_2sm(sa, &mapA, lbar, k, c0);
+          if (act0) tf2::tma_load_2d_2sm(sa + tf2::A_BYTES, &mapB, lbar, k, r0);
+          if (act1) tf2::tma_load_2d_2sm(sa + tf2::A_BYTES + tf2::BH_BYTES, &mapB, lbar, k, r1);
+        }
+        sa += tf2::STAGE_BYTES;
+        if (++stage == tf2::STAGES) {
+          stage = 0;
+          phase ^= 1;
+          sa = sgen;
+        }
+      };
       for (int j = 0;; ++j) {
         int b0, b1, c0;
         if (!item_at(j, b0, b1, c0)) break;
         const bool has1 = b1 < nblk;
         const int kend0 = min((b0 + 1) * tf2::BN, np);
         const int kend = has1 ? min((b1 + 1) * tf2::BN, np) : kend0;
-        for (int k = 0; k < kend; k += tf2::BK) {
-          const bool act0 = k < kend0;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = sgen + stage * tf2::STAGE_BYTES;
-          const uint32_t lbar = tf2::map_to_cta(smem_u32(&full_bar[stage]), 0);
-          tf2::mbar_expect_tx_cluster(
-              lbar, tf2::A_BYTES + (act0 ? tf2::BH_BYTES : 0) + (has1 ? tf2::BH_BYTES : 0));
-          tf2::tma_load_2d_2sm(sa, &mapA, lbar, k, c0);
-          // diagonal block, kk columns in: the MMA takes N = 256 - kk, i.e. the first 128 - kk/2 rows of either
-          // CTA's tile, and accumulator column c must stay physical row c: the second CTA's box starts kk/2 rows
-          // earlier (its first rows are then physical rows 128 - kk/2 ..)
-          const int sh0 = (shrink && k > b0 * tf2::BN) ? int(cta_rank) * ((k - b0 * tf2::BN) >> 1) : 0;
-          const int sh1 = (shrink && k > b1 * tf2::BN) ? int(cta_rank) * ((k - b1 * tf2::BN) >> 1) : 0;
-          if (act0)
-            tf2::tma_load_2d_2sm(sa + tf2::A_BYTES, &mapB, lbar, k,
-                                 b0 * tf2::BN + int(cta_rank) * (tf2::BN / 2) - sh0);
-          if (has1)
-            tf2::tma_load_2d_2sm(sa + tf2::A_BYTES + tf2::BH_BYTES, &mapB, lbar, k,
-                                 b1 * tf2::BN + int(cta_rank) * (tf2::BN / 2) - sh1);
-          if (++stage == tf2::STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+        const int kd0 = b0 * tf2::BN, kd1 = has1 ? min(b1 * tf2::BN, kend) : kend;
+        const int r0 = b0 * tf2::BN + half, r1 = b1 * tf2::BN + half;
+        // diagonal block, kk columns in: the MMA takes N = 256 - kk, i.e. the first 128 - kk/2 rows of either
+        // CTA's tile, and accumulator column c must stay physical row c: the second CTA's box starts kk/2 rows
+        // earlier (its first rows are then physical rows 128 - kk/2 ..)
+        const int dsh = (shrink && cta_rank != 0) ? tf2::BK / 2 : 0;   // rows the box moves up per diagonal stage
+        int k = 0;
+        for (; k < kd0; k += tf2::BK) do_stage(k, c0, true, has1, r0, r1);
+        for (int sh = 0; k < kend0; k += tf2::BK, sh += dsh) do_stage(k, c0, true, has1, r0 - sh, r1);
+        if (has1) {
+          for (; k < kd1; k += tf2::BK) do_stage(k, c0, false, true, 0, r1);
+          for (int sh = 0; k < kend; k += tf2::BK, sh += dsh) do_stage(k, c0, false, true, 0, r1 - sh);
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {   // ===== MMA issuer (leader CTA only) =====
+    if (leader) {   // ===== MMA issuer (leader CTA only) =====
       // D=f32, A=B=f16, K-major, N=256, M=256 (two SMs).  In the diagonal 256 x 256 block of a row block the rows
-      // above the stage's first column are zero and sit at the end of the block (k_make_tf32): N shrinks by 32
-      // per stage there, so the diagonal blocks cost 17/32 of a full block instead of 1 (BBO_TF32_FULL_DIAG=1: off)
+      // above the stage's first column are zero and sit at the end of the block (k_make_f16): N shrinks by 32
+      // per stage there, so the diagonal blocks cost 17/32 of a full block instead of 1 (BBO_TF32_FULL_DIAG=1: off).
+      //
+      // ONE thread feeds the tensor cores of both SMs, and it used to be what bounded the kernel: ~155 SASS
+      // instructions per stage (shared-window address conversions, descriptor construction, the diagonal-block test,
+      // a vote loop around every uniform-datapath instruction because the compiler could not see a single-lane
+      // region) against 512 tensor-pipe cycles of work -- the pipe was busy 65 % of the time with TF32 and with
+      // binary16 operands alike.  Now the whole warp runs the loop and an elect.sync lane issues; barrier addresses
+      // and the stage-0 descriptor are computed once, a stage advances them by constants, and an item is walked in
+      // three phases (both blocks full / first block diagonal / second block alone) so that no per-stage test of the
+      // diagonal remains.
+      const bool el = tf2::elect_one();
       const uint32_t idesc_base = (1u << 4) | (uint32_t(256 >> 4) << 24);   // D = f32, A = B = f16 (format 0)
-      const uint32_t idesc = idesc_base | (uint32_t(tf2::BN >> 3) << 17);
-      auto idesc_for = [&](int k, int b) -> uint32_t {
-        const int kk = k - b * tf2::BN;              // columns into the diagonal block (multiple of 16), < 0 above it
-        if (!shrink || kk <= 0) return idesc;
-        return idesc_base | (uint32_t((tf2::BN - kk) >> 3) << 17);
-      };
+      const uint32_t idesc_full = idesc_base | (uint32_t(tf2::BN >> 3) << 17);
+      constexpr uint32_t ID_STEP = uint32_t(tf2::BK >> 3) << 17;            // N shrinks by BK per diagonal stage
+      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+      const uint32_t tfull0 = smem_u32(&tfull_bar[0]), tempty0 = smem_u32(&tempty_bar[0]);
+      const uint64_t desc0 = tfp::make_desc64(sbase);
+      constexpr uint64_t STAGE_D = uint64_t(tf2::STAGE_BYTES >> 4), A_D = uint64_t(tf2::A_BYTES >> 4),
+                         BH_D = uint64_t(tf2::BH_BYTES >> 4);
       int stage = 0;
       uint32_t phase = 0, acc_phase = 0, acc1_phase = 0;   // the second accumulator idles in an item without b1
+      uint64_t adesc = desc0;
+      const uint32_t tm0 = tmem_base, tm1 = tmem_base + uint32_t(tf2::BN);
+      // one stage: wait for the operands, 2 MMAs (K = 2 x 16) per active accumulator, release the stage
+      auto do_stage = [&](bool act0, bool act1, uint32_t id0, uint32_t id1, uint32_t accum) {
+        tf2::mbar_wait_addr(full0 + uint32_t(stage) * 8u, phase);
+        tc_fence_after();
+        if (el) {
+          if (act0) {
+            tf2::mma_f16_2sm(tm0, adesc, adesc + A_D, id0, accum);
+            tf2::mma_f16_2sm(tm0, adesc + 2, adesc + A_D + 2, id0, 1u);
+          }
+          if (act1) {
+            tf2::mma_f16_2sm(tm1, adesc, adesc + A_D + BH_D, id1, accum);
+            tf2::mma_f16_2sm(tm1, adesc + 2, adesc + A_D + BH_D + 2, id1, 1u);
+          }
+          tf2::commit_2sm_addr(empty0 + uint32_t(stage) * 8u);       // frees the stage in both CTAs
+        }
+        adesc += STAGE_D;
+        if (++stage == tf2::STAGES) {
+          stage = 0;
+          phase ^= 1;
+          adesc = desc0;
+        }
+      };
       for (int j = 0;; ++j) {
         int b0, b1, c0;
         if (!item_at(j, b0, b1, c0)) break;
         const bool has1 = b1 < nblk;
         const int kend0 = min((b0 + 1) * tf2::BN, np);
         const int kend = has1 ? min((b1 + 1) * tf2::BN, np) : kend0;
-        mbar_wait(&tempty_bar[0], acc_phase ^ 1);
-        if (has1) mbar_wait(&tempty_bar[1], acc1_phase ^ 1);
+        const int kd0 = b0 * tf2::BN, kd1 = has1 ? min(b1 * tf2::BN, kend) : kend;   // starts of the diagonal blocks
+        tf2::mbar_wait_addr(tempty0, acc_phase ^ 1);
+        if (has1) tf2::mbar_wait_addr(tempty0 + 8u, acc1_phase ^ 1);
         tc_fence_after();
-        for (int k = 0; k < kend; k += tf2::BK) {
-          const bool act0 = k < kend0;
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = sbase + stage * tf2::STAGE_BYTES;
-          const uint64_t adesc = tfp::make_desc64(sa);
-          if (act0) {
-            const uint64_t bdesc = tfp::make_desc64(sa + tf2::A_BYTES);
-            const uint32_t id0 = idesc_for(k, b0);
-#pragma unroll
-            for (int kk = 0; kk < tf2::BK / tf2::UK; ++kk)
-              tf2::mma_f16_2sm(tmem_base, adesc + uint64_t(kk * 2), bdesc + uint64_t(kk * 2), id0,
-                                (k | kk) != 0 ? 1u : 0u);
-          }
-          if (has1) {
-            const uint64_t bdesc = tfp::make_desc64(sa + tf2::A_BYTES + tf2::BH_BYTES);
-            const uint32_t id1 = idesc_for(k, b1);
-#pragma unroll
-            for (int kk = 0; kk < tf2::BK / tf2::UK; ++kk)
-              tf2::mma_f16_2sm(tmem_base + uint32_t(tf2::BN), adesc + uint64_t(kk * 2), bdesc + uint64_t(kk * 2),
-                                id1, (k | kk) != 0 ? 1u : 0u);
-          }
-          tf2::commit_2sm(&empty_bar[stage]);                        // frees the stage in both CTAs
-          if (k + tf2::BK == kend0) tf2::commit_2sm(&tfull_bar[0]);   // block b0 complete in both halves
-          if (++stage == tf2::STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+        int k = 0;
+        // both blocks below their diagonal
+        for (; k < kd0; k += tf2::BK) do_stage(true, has1, idesc_full, idesc_full, k != 0 ? 1u : 0u);
+        // block b0 on its diagonal (N shrinks stage by stage), b1 still full
+        uint32_t id0 = idesc_full;
+        for (; k < kend0; k += tf2::BK) {
+          do_stage(true, has1, id0, idesc_full, k != 0 ? 1u : 0u);
+          if (shrink) id0 -= ID_STEP;
         }
+        if (el) tf2::commit_2sm_addr(tfull0);                        // block b0 complete in both halves
         if (has1) {
-          tf2::commit_2sm(&tfull_bar[1]);
+          // b1 alone: full below its diagonal (legacy form only: b1 > b0 + 1), then its diagonal
+          for (; k < kd1; k += tf2::BK) do_stage(false, true, idesc_full, idesc_full, 1u);
+          uint32_t id1 = idesc_full;
+          for (; k < kend; k += tf2::BK) {
+            do_stage(false, true, idesc_full, id1, 1u);
+            if (shrink) id1 -= ID_STEP;
+          }
+          if (el) tf2::commit_2sm_addr(tfull0 + 8u);
           acc1_phase ^= 1;
         }
         acc_phase ^= 1;
