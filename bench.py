@@ -227,16 +227,36 @@ def run_reference(a):
 
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock, power and clocks-event reasons of one GPU sampled DURING the timed region: NVML from a thread every
+    ~2 ms (nvidia-smi -lms needs ~100 ms to start and 50 ms per sample, the timed region of a default run is ~100 ms);
+    nvidia-smi is the fallback when NVML cannot be loaded."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.rows = []          # (sm_mhz, max_mhz, watts, set of reasons)
         self.proc = None
+        self.nvml = None
+        self.stop_flag = threading.Event()
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it lists plain indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = self.index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                phys = int(vis.split(",")[self.index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:  # noqa: BLE001
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
@@ -246,34 +266,56 @@ class ClockSampler:
         except Exception:  # noqa: BLE001
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _poll(self):
+        nv = self.nvml
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                self.rows.append((sm, mx, pw, {k for k, b in bits.items() if mask & b}))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:  # noqa: BLE001
-            self.proc.kill()
-        sm, mx, reasons, pw = [], [], set(), []
+    def _read(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for line in self.proc.stdout:
+            r = [c.strip() for c in line.split(",")]
             if len(r) < 7:
                 continue
             try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-                pw.append(float(r[2]))
+                self.rows.append((float(r[0]), float(r[1]), float(r[2]),
+                                  {nm for nm, v in zip(names, r[3:7]) if v.lower().startswith("active")}))
             except ValueError:
                 continue
-            for nm, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+    def stop(self):
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML, no nvidia-smi"]}
+        self.stop_flag.set()
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
+        else:
+            self.t.join(timeout=1)
+        rows = list(self.rows)
+        sm = [r[0] for r in rows]
+        reasons = set()
+        for r in rows:
+            reasons |= r[3]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+                "sm_max_mhz": max(r[1] for r in rows) if rows else None,
+                "power_w_max": max(r[2] for r in rows) if rows else None, "samples": len(rows),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi", "reasons": sorted(reasons)}
 
 
 def load_json(path):
