@@ -9,14 +9,14 @@
 //
 // Kernels (one default per shape; the A/B generations of round 1 were removed in round 2):
 //   K* producers (correlations of a chunk rounded to binary16, fused with mu = c + K* alpha from the float32 values)
-//     k_kstar_umma       d <= 30      tcgen05 kind::tf32, one 3xTF32 contraction over concatenated hi/lo rows,
-//                                     TMA operand loads, TMEM accumulator ring, TMA tensor stores
-//     k_kstar_umma_stream 30 < d <= 126 the same contraction with BOTH operands streamed in 32-word boxes
-//     k_kstar_mma2       (mma.sync 3xTF32 with the two augmentation columns; A/B reference for the two above)
+//     k_kstar_umma       d <= 126     tcgen05 kind::tf32, 3xTF32 contraction by pairing the k-steps of [hi | lo]
+//                                     operand rows; candidate tile resident, observation boxes in a TMA ring, TMEM
+//                                     accumulator ring, TMA tensor stores
+//     k_kstar_mma2       (mma.sync 3xTF32 with the two augmentation columns; A/B reference for the one above)
 //     k_kstar_f32_fast   126 < d <= 192 CUDA cores, expanded form;   k_kstar_f32  any d, exact-difference form
 //   n^2 panel (V = L^-1 k* is never written: the epilogue squares and row-sums the accumulators)
 //     k_vnorm_tf32_2sm<true>   persistent CTA pairs walking a work list (k_panel_schedule): default while the
-//                              TF32 L^-1 fits in L2 (n <= ~4500)
+//                              binary16 L^-1 fits in L2 (n <= ~6300)
 //     k_vnorm_tf32_2sm<false>  one CTA pair per candidate tile pair, lock-step over the row pairs (n = 8192)
 //     k_vnorm_tf32_pair<1>     single-CTA form for chunks with an odd number of 128-candidate tiles
 //   warp roles of the panel kernels: warp 0 TMA producer (cp.async.bulk.tensor.2d, 64-byte swizzle, mbarrier
@@ -1251,28 +1251,26 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 // ------------------------------------------------------------------------------------------
-// K* producer on tcgen05 (default for d <= 30): the augmented 3xTF32 contraction of k_kstar_mma2 on
-// the 5th-generation tensor cores.  The three partial products are ONE contraction of length 3 dk over
-// concatenated operand rows,
-//     candidates   Aop[c] = [ hi(u) | hi(u) | lo(u) | 0.. ]      u = the augmented candidate row of k_kstar_mma2
-//     observations Bop[j] = [ hi(b) | lo(b) | hi(b) | 0.. ]      b as in k_prescale_aug
-// so Aop[c] . Bop[j] = u_hi b_hi + u_hi b_lo + u_lo b_hi is the finished exponent (RBF) / squared distance
-// (Matern).  Persistent CTAs (one per SM), 576 threads, warp specialised:
-//   warp 0     TMA producer: the 128-candidate A tile once per tile, 128-observation B tiles in a 2-stage ring
-//              (SWIZZLE_128B boxes of 128 rows x 32 words)
+// K* producer on tcgen05 (d <= 126): the augmented 3xTF32 contraction of k_kstar_mma2 on the 5th-generation tensor
+// cores.  Operand rows hold the TF32 hi and lo parts of the augmented vectors side by side,
+//     candidates   Aop[c] = [ hi(u) | lo(u) | 0.. ]      u = the augmented candidate row of k_kstar_mma2
+//     observations Bop[j] = [ hi(b) | lo(b) | 0.. ]      b as in k_prescale_aug
+// (2 dk words, padded to 32-word boxes) and the three partial products u_hi b_hi + u_lo b_hi + u_hi b_lo -- the
+// finished exponent (RBF) / squared distance (Matern) -- are formed by PAIRING k-steps: a `hi` step of an observation
+// box meets the candidate's hi and lo steps, a `lo` step its hi step.  Persistent CTAs (one per SM), 576 threads:
+//   warp 0     TMA producer: the 128-candidate A tile once per tile (two tiles resident when they fit: the next one
+//              loads under this one's MMAs), observation boxes (SWIZZLE_128B, 128 rows x 32 words) through a ring
 //   warp 1     one thread issues tcgen05.mma kind::tf32, M = 128 x N = 128 x K = 8, 3 dk / 8 instructions per
-//              128 x 128 block; four 128-column TMEM accumulators in a ring, so the tensor core runs up to four
-//              blocks ahead of the epilogue
+//              128 x 128 block, fully unrolled on the template parameter DKS = dk / 8 (every descriptor = base +
+//              constant; with run-time bounds this thread was the bottleneck); four 128-column TMEM accumulators in a
+//              ring, so the tensor core runs up to four blocks ahead of the epilogue
 //   warps 2-17 epilogue, one (TMEM lane quarter, 32-column slab) per warp: tcgen05.ld 32 lanes x 32 columns ->
 //              ex2 (Matern: sqrt, cubic, ex2) -> mu += K* alpha (alpha staged one block ahead by cp.async) ->
-//              round to TF32 (integer pipe) -> st.shared.v4 into a 128-byte-swizzled 32 x 32 staging tile ->
+//              cvt.rn.f16x2.f32 -> st.shared.v4 into one of two 64-byte-swizzled 32 x 32 staging tiles ->
 //              TMA tensor store (cp.async.bulk.tensor ... bulk_group)
-// so every K* byte leaves the SM as part of a full 128-byte line (the mma.sync forms scatter 8-byte stores)
-// and the kernel runs at the HBM write rate of the K* chunk (4.6 TB/s under ncu; the remaining stalls are the
-// TMA store queue and the accumulator hand-over).  mu = c + the four slab partials in a fixed order
-// (deterministic).  Measured alternatives, same launch: 8 epilogue warps with a register software pipeline
-// (TMEM load of slab g+1 under the arithmetic of slab g) 130 us, the same with the B tiles TMA-multicast over a
-// 2-CTA cluster 131 us, this form 122 us, third mma.sync form 166 us.
+// so every K* byte leaves the SM as part of a full line (the mma.sync forms scatter 8-byte stores).
+// mu = c + s2 x the four slab partials in a fixed order (deterministic).  History and counters:
+// profiles/kstar_umma_r02_ncu_full.md (72 us per 37888 x 4096 chunk; 122 us in round 1 with float32 output).
 // ------------------------------------------------------------------------------------------
 namespace ku {
 constexpr int BM = 128, BN = 128, BOXK = 32;

@@ -498,6 +498,13 @@ def run_b200(a):
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = lib.bbo_launch_count() - l0
     clk = clocks.stop() if rank == 0 else None
+    if clk is not None:
+        # context for the reader: what the driver's own peak measurement saw on this pool under tensor load
+        mpk = load_json(os.path.join(ROOT, "MEASURED_PEAKS.json")) or {}
+        cul = mpk.get("clocks_under_load")
+        if cul:
+            clk["measured_peaks_clocks_under_load"] = {k: cul.get(k) for k in ("sm_mhz_median", "sm_max_mhz",
+                                                                              "power_w_max", "throttled")}
     value = q_total * a.steps / (ms * 1e-3)
     # collective cost: `collective_in_step_ms` is what the events around pack / all-gather / merge saw inside the timed
     # steps -- it includes waiting for the slowest rank to ARRIVE (per-chip power caps make the ranks' steps differ by
