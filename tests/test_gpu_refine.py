@@ -142,3 +142,47 @@ def test_refine_ties_resolve_to_the_lowest_index(cuda_device):
     assert torch.equal(ir, i64)
     lo = np_(i64).reshape(4, 2)          # four best rows, each followed by its copy: lower index first
     assert np.all(lo[:, 1] == lo[:, 0] + 5000) and np.all(lo[:, 0] < 5000)
+
+
+@pytest.mark.parametrize("order", ["ascending", "descending", "blocks"])
+def test_selection_on_pools_sorted_by_score(order, cuda_device):
+    """Worst cases of the threshold-filtered selection (k_acq_eval / k_filter_heavy / k_merge_level /
+    k_merge_survivors): a pool sorted by ASCENDING score makes every candidate of every chunk beat the running list
+    (all blocks take the heavy path, thousands of survivors per chunk, every chunk), descending order empties the
+    filter after the short first chunk, and `blocks` mixes light and heavy blocks inside one segment.  The selection
+    must be the float64 one in all three precisions, with several chunks per pool."""
+    n, d, q, k = 600, 20, 60000, 8
+    p, X, y = synth_problem(2024, n, d, kind=O.RBF, noise=1e-3, ls_mean=-0.3)
+    gp = gp_from_params(p, X, y, q_chunk=8192)          # 8 chunks
+    acq = B.UCB()
+    pool = torch.as_tensor(np.random.default_rng(3).random((q, d))).cuda()
+    _, _, _, _, sc = gp.score_pool(pool, acq, k, precision="fp64", return_all=True)
+    idx = torch.argsort(sc)
+    if order == "descending":
+        idx = idx.flip(0)
+    elif order == "blocks":                              # ascending runs of 300 candidates between shuffled stretches
+        perm = torch.randperm(q, generator=torch.Generator().manual_seed(1)).cuda()
+        idx = torch.where((torch.arange(q, device="cuda") // 300) % 2 == 0, idx, perm)
+        idx = torch.unique(idx)                          # a valid (shorter) pool of distinct candidates
+    pool2 = pool[idx].contiguous()
+    s64, i64 = gp.score_pool(pool2, acq, k, precision="fp64")
+    want = torch.argsort(sc[idx], descending=True, stable=True)[:k]
+    assert torch.equal(i64, want)
+    st, it = gp.score_pool(pool2, acq, k, precision="tf32")
+    assert len(set(np_(it).tolist()) & set(np_(i64).tolist())) >= k - 2      # TF32-accurate scores
+    sr, ir = gp.score_pool(pool2, acq, k, precision="tf32+refine")
+    assert gp.refine_certificate()["certified"]
+    assert torch.equal(ir, i64)
+    assert np.allclose(np_(sr), np_(s64), rtol=1e-9, atol=0)
+    # k = 32 (short-list of 256): the widest lists the merge kernels see
+    s64b, i64b = gp.score_pool(pool2, acq, 32, precision="fp64")
+    srb, irb = gp.score_pool(pool2, acq, 32, precision="tf32+refine")
+    assert gp.refine_certificate()["certified"]
+    assert torch.equal(irb, i64b)
+    # automatic chunking: a short first chunk (one wave) followed by one long chunk
+    gp2 = gp_from_params(p, X, y)
+    sr2, ir2 = gp2.score_pool(pool2, acq, k, precision="tf32+refine")
+    assert gp2.refine_certificate()["certified"]
+    assert torch.equal(ir2, i64)
+    st2, it2 = gp2.score_pool(pool2, acq, k, precision="tf32")
+    assert torch.equal(it2, it) and torch.equal(st2, st)          # chunking does not change a bit
