@@ -1880,8 +1880,12 @@ static int sm_count() {
   return sms[dev];
 }
 
+// `side_sms` > 0: the producer runs BESIDE a panel that leaves that many SMs free (see score_tf32_pipeline): its grid
+// is capped there and launched as clusters of two CTAs so that it occupies whole TPCs (the panel's CTA pairs need both
+// SMs of a TPC).
 static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf32Scratch& t, int buf,
-                        const void* Xq, int xq_is_f32, int64_t qc, int64_t qc_pad, double* mu_chunk, cudaStream_t st) {
+                        const void* Xq, int xq_is_f32, int64_t qc, int64_t qc_pad, double* mu_chunk, cudaStream_t st,
+                        int side_sms = 0) {
   const int64_t np = w.np;
   prof_begin(kProfKstar, st);
   if (use_kstar_umma(s.h.d)) {
@@ -1902,7 +1906,9 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
     rc = make_map(&mapO, t.Ks[buf], qc_pad, np, 32, 32);        // 32 candidates x 32 binary16 values (64-byte rows)
     if (rc != BBO_OK) return rc;
     const int tiles = int(qc_pad / ku::BM);
-    const int grid = tiles < sm_count() ? tiles : sm_count();
+    int grid = tiles < sm_count() ? tiles : sm_count();
+    const bool side = side_sms >= 2 && grid > side_sms;
+    if (side) grid = side_sms & ~1;
     const double* hyp = s.hyp;
     ku::Plan pl = ku::plan(nbox);
     if (const char* e = getenv("BBO_KSTAR_NA")) pl.na = atoi(e);         // tuning aids (the plan stays within the budget
@@ -1920,12 +1926,26 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
       BBO_CUDA_CHECK(cudaFuncSetAttribute(k_kstar_umma<true, DKS_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                           int(most)));                                                              \
     }                                                                                                               \
+    cudaLaunchConfig_t kcfg = {};                                                                                   \
+    kcfg.gridDim = dim3(unsigned(grid));                                                                            \
+    kcfg.blockDim = dim3(ku::THREADS);                                                                              \
+    kcfg.dynamicSmemBytes = pl.bytes;                                                                               \
+    kcfg.stream = st;                                                                                               \
+    cudaLaunchAttribute kat[1];                                                                                     \
+    kat[0].id = cudaLaunchAttributeClusterDimension;                                                                \
+    kat[0].val.clusterDim.x = side ? 2 : 1;                                                                         \
+    kat[0].val.clusterDim.y = 1;                                                                                    \
+    kat[0].val.clusterDim.z = 1;                                                                                    \
+    kcfg.attrs = kat;                                                                                               \
+    kcfg.numAttrs = 1;                                                                                              \
+    const int np_k = int(np), d_k = s.h.d;                                                                          \
+    const float* al_k = t.alpha32;                                                                                  \
     if (matern)                                                                                                     \
-      k_kstar_umma<true, DKS_><<<unsigned(grid), ku::THREADS, pl.bytes, st>>>(                                      \
-          mapA, mapB, mapO, int(np), tiles, nbox, dk, s.h.d, pl.na, pl.ring, pl.stg2, hyp, t.alpha32, mu_chunk);    \
+      BBO_CUDA_CHECK(cudaLaunchKernelEx(&kcfg, k_kstar_umma<true, DKS_>, mapA, mapB, mapO, np_k, tiles, nbox, dk,   \
+                                        d_k, pl.na, pl.ring, pl.stg2, hyp, al_k, mu_chunk));                        \
     else                                                                                                            \
-      k_kstar_umma<false, DKS_><<<unsigned(grid), ku::THREADS, pl.bytes, st>>>(                                     \
-          mapA, mapB, mapO, int(np), tiles, nbox, dk, s.h.d, pl.na, pl.ring, pl.stg2, hyp, t.alpha32, mu_chunk);    \
+      BBO_CUDA_CHECK(cudaLaunchKernelEx(&kcfg, k_kstar_umma<false, DKS_>, mapA, mapB, mapO, np_k, tiles, nbox, dk,  \
+                                        d_k, pl.na, pl.ring, pl.stg2, hyp, al_k, mu_chunk));                        \
   } break;
     switch (dk / 8) {
       BBO_KSTAR_UMMA(1)
@@ -2031,8 +2051,25 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
 
 // *vpart_out / *nsplit_out: where the partial sums of this chunk are and how k_acq / k_acq_topk add them (4 = the
 // four fixed slots of `vpart`; -nblk = one slot per row block in the persistent panel's own buffer).
+// Does a chunk of qc_pad candidates run on the persistent form of the panel (launch_panel's own conditions)?
+static bool panel_persists(int64_t np, int64_t qc_pad, int reserve_sms) {
+  static const bool clus = getenv("BBO_TF32_NO_CLUSTER") == nullptr;
+  static const bool no_persist = getenv("BBO_TF32_NO_PERSIST") != nullptr;
+  static const int64_t l2_mb = getenv("BBO_TF32_PERSIST_MAX_MB") ? atoll(getenv("BBO_TF32_PERSIST_MAX_MB")) : 80;
+  const int64_t tiles = qc_pad / tf::BM, nblk = ceil_div(np, tf::BN);
+  if (!clus || no_persist || tiles % 2 != 0) return false;
+  const int ntp = int(tiles / 2), nrp = int((nblk + 1) / 2), nitems = ntp * nrp;
+  const int pairs = (sm_count() - reserve_sms) / 2;
+  const int nc = nitems < pairs ? nitems : pairs;
+  const int maxj = (ntp * nrp + nc - 1) / nc * 4 + 8;
+  return np * np * int64_t(sizeof(__half)) <= (l2_mb << 20) && nblk >= 2 && nblk <= 32 && nc <= 96 &&
+         int64_t(nc) * maxj <= kSchedInts;
+}
+
+// `reserve_sms`: SMs the persistent form leaves to the K* producer of the next chunk (0 = none).
 static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf32Scratch& t, int buf,
-                        int64_t qc_pad, double* vpart, int* nsplit_out, double** vpart_out, cudaStream_t st) {
+                        int64_t qc_pad, double* vpart, int* nsplit_out, double** vpart_out, cudaStream_t st,
+                        int reserve_sms = 0) {
   const int64_t np = w.np;
   // chunks with an even number of 128-candidate tiles run on CTA pairs (cta_group::2); BBO_TF32_NO_CLUSTER=1 sends
   // every chunk through the single-CTA kernel that otherwise serves odd tile counts (same bits: tests compare them)
@@ -2089,7 +2126,8 @@ static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
     // CTA pairs: one per SM pair, or one per item when the chunk has fewer items than that (a small pool spreads the
     // row pairs of its few tile pairs over the chip)
     const int nitems = ntp * nrp;
-    const int nc = nitems < sm_count() / 2 ? nitems : sm_count() / 2;
+    const int pairs = (sm_count() - reserve_sms) / 2;
+    const int nc = nitems < pairs ? nitems : pairs;
     // list capacity: four times the mean item count (the lists hold ntp * nrp items in total, so with full lists
     // skipped by the scheduler every item finds a place)
     const int maxj = (ntp * nrp + nc - 1) / nc * 4 + 8;
@@ -2230,6 +2268,14 @@ int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const vo
     return left < full ? left : full;
   };
   auto chunk_ptr = [&](int64_t i) { return static_cast<const char*>(Xq) + size_t(chunk_start(i)) * d * esz; };
+  // Side-by-side mode (BBO_TF32_KSTAR_SMS = SMs for the producer): while panel(i) runs on a persistent grid that
+  // leaves those SMs free, K*(i+1) runs on them, instead of on the whole chip in the gap between two panels.
+  static const int kstar_sms = getenv("BBO_TF32_KSTAR_SMS") ? atoi(getenv("BBO_TF32_KSTAR_SMS")) : 0;
+  auto side_for = [&](int64_t i) -> int {   // SMs reserved while panel(i) and K*(i+1) run
+    if (kstar_sms < 2 || !two_streams || !use_kstar_umma(d)) return 0;
+    const int64_t qc = chunk_len(i);
+    return panel_persists(w.np, ceil_div(qc, 128) * 128, kstar_sms) ? kstar_sms : 0;
+  };
   {
     const int64_t qc = chunk_len(0);
     mark(aux->sk);
@@ -2253,7 +2299,7 @@ int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const vo
       const int64_t qn = chunk_len(i + 1);
       mark(aux->sk);
       rc = launch_kstar(s, w, t, nb, chunk_ptr(i + 1), xq_is_f32, qn, ceil_div(qn, 128) * 128, t.mu[(i + 1) % 3],
-                        aux->sk);
+                        aux->sk, side_for(i));
       if (rc != BBO_OK) return rc;
       mark(aux->sk);
       if (two_streams) BBO_CUDA_CHECK(cudaEventRecord(aux->kdone[nb], aux->sk));
@@ -2267,7 +2313,8 @@ int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const vo
     int nsplit = 1;
     double* vpart = nullptr;
     mark(st);
-    rc = launch_panel(s, w, t, buf, ceil_div(qc, 128) * 128, w.vpart + int64_t(buf) * 4 * w.qp, &nsplit, &vpart, st);
+    rc = launch_panel(s, w, t, buf, ceil_div(qc, 128) * 128, w.vpart + int64_t(buf) * 4 * w.qp, &nsplit, &vpart, st,
+                      i + 1 < nchunk ? side_for(i) : 0);
     if (rc != BBO_OK) return rc;
     mark(st);
     if (two_streams) {
