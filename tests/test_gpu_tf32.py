@@ -134,14 +134,15 @@ from _gpu_helpers import gp_from_params, synth_problem
 out = {}
 for n, d, kind in [(2100, 20, O.RBF), (600, 24, O.MATERN52)]:
     p, X, y = synth_problem(1000 + n, n, d, kind=kind, noise=1e-4, ls_mean=0.2)
-    Xq = torch.as_tensor(np.random.default_rng(n).random((3000, d))).cuda()
+    Xq = torch.as_tensor(np.random.default_rng(n).random((50000 if n > 2000 else 3000, d))).cuda()   # 2 chunks / 1
     gp = gp_from_params(p, X, y)
     s, i = gp.score_pool(Xq, B.EI(float(y.max())), 8, precision="tf32")
     out[str(n)] = [s.cpu().tolist(), i.cpu().tolist()]
 print("RESULT" + json.dumps(out))
 """ % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
     res = {}
-    for tag, extra in [("umma", {}), ("mma", {"BBO_KSTAR_NO_UMMA": "1"}), ("lockstep", {"BBO_TF32_NO_PERSIST": "1"})]:
+    for tag, extra in [("umma", {}), ("mma", {"BBO_KSTAR_NO_UMMA": "1"}), ("lockstep", {"BBO_TF32_NO_PERSIST": "1"}),
+                       ("rounds", {"BBO_SELECT_ROUNDS": "1"}), ("side", {"BBO_TF32_KSTAR_SMS": "24"})]:
         env = dict(os.environ, **extra)
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr[-2000:]
@@ -156,3 +157,8 @@ print("RESULT" + json.dumps(out))
         # add the same numbers in the same association: bit-identical scores and indices
         sl, il = res["lockstep"][key]
         assert il == iu and sl == su
+        # the round-based selection (fallback of the threshold filter) and the side-by-side K* / panel schedule change
+        # neither a score nor the selection
+        for other in ("rounds", "side"):
+            so, io = res[other][key]
+            assert io == iu and so == su, other
