@@ -759,7 +759,8 @@ int topk_merge(const double* score, const int64_t* index, int64_t m, int k, doub
 // ==========================================================================================
 // workspace + drivers
 // ==========================================================================================
-static int64_t round_chunk(int64_t q_chunk) { return ceil_div(q_chunk < 128 ? 128 : q_chunk, 128) * 128; }
+// chunks are padded to 256 candidates: the tensor-core panel works on PAIRS of 128-candidate tiles (cta_group::2)
+static int64_t round_chunk(int64_t q_chunk) { return ceil_div(q_chunk < 256 ? 256 : q_chunk, 256) * 256; }
 
 // Number of row-tile splits of the variance panel.  It must depend on n ONLY: the partial sums of
 // a candidate are then associated identically for every chunking / sharding of the pool, which is

@@ -18,7 +18,7 @@
 //     k_vnorm_tf32_2sm<true>   persistent CTA pairs walking a work list (k_panel_schedule): default while the
 //                              binary16 L^-1 fits in L2 (n <= ~6300)
 //     k_vnorm_tf32_2sm<false>  one CTA pair per candidate tile pair, lock-step over the row pairs (n = 8192)
-//     k_vnorm_tf32_pair<1>     single-CTA form for chunks with an odd number of 128-candidate tiles
+//   (chunks are padded to 256 candidates, so every chunk runs on CTA pairs; the single-CTA forms are gone)
 //   warp roles of the panel kernels: warp 0 TMA producer (cp.async.bulk.tensor.2d, 64-byte swizzle, mbarrier
 //   ring), warp 1 one thread issuing tcgen05.mma kind::f16 (M = 128 per CTA x N = 256 x K = 16, accumulators in
 //   TMEM, two row blocks per K* stage), warps 2-5 epilogue (tcgen05.ld.32x32b.x32 -> square + row-sum).
@@ -92,23 +92,10 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
-                                               uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
-      : "memory");
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"(cta_mask)
                : "memory");
 }
 __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -117,15 +104,6 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -218,197 +196,11 @@ __device__ __forceinline__ double panel_factor(const double* __restrict__ hyp, i
   return s2 * s2 * double(__ldg(lscale));
 }
 
-// CL = 2: clusters of two CTAs (adjacent candidate tiles, same row blocks).  Each CTA loads HALF of
-// every L^-1 tile and TMA-multicasts it to both, so the B operand crosses L2->SM once per cluster;
-// a stage is released to the producers only when BOTH tensor cores have consumed it
-// (tcgen05.commit multicast onto both CTAs' empty barriers, count 2).
-template <int CL>
-__global__ void __launch_bounds__(tf::THREADS, 1)
-k_vnorm_tf32_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int np,
-                  int64_t qc_pad, double* __restrict__ vpart, const double* __restrict__ hyp, int d,
-                  const float* __restrict__ lscale) {
-  using namespace tf;
-  uint32_t cta_rank = 0;
-  if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[tfp::STAGES], empty_bar[tfp::STAGES], tfull_bar[2], tempty_bar[2];
-  __shared__ uint32_t tmem_base_sh;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  const int c0 = blockIdx.x * tfp::BM;
-  const int nblk = (np + tfp::BN - 1) / tfp::BN;
-  const int S = gridDim.y;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < tfp::STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CL);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 128);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
-                 "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (CL > 1) {   // peers' barriers must be initialised before any remote arrive / multicast lands
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-  }
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_sh;
-
-  if (warp == 0) {
-    if (lane == 0) {   // ===== TMA producer =====
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int b0 = blockIdx.y; b0 < nblk; b0 += 2 * S) {
-        const int b1 = b0 + S;
-        const bool has1 = b1 < nblk;
-        const int kend0 = min((b0 + 1) * tfp::BN, np);
-        const int kend = has1 ? min((b1 + 1) * tfp::BN, np) : kend0;
-        for (int k = 0; k < kend; k += tfp::BK) {
-          const bool act0 = k < kend0;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = sgen + stage * tfp::STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], tfp::A_BYTES + (act0 ? tfp::B_BYTES : 0) + (has1 ? tfp::B_BYTES : 0));
-          tma_load_2d(sa, &mapA, &full_bar[stage], k, c0);
-          if (CL == 1) {
-            if (act0) tma_load_2d(sa + tfp::A_BYTES, &mapB, &full_bar[stage], k, b0 * tfp::BN);
-            if (has1) tma_load_2d(sa + tfp::A_BYTES + tfp::B_BYTES, &mapB, &full_bar[stage], k, b1 * tfp::BN);
-          } else {   // my half of each L^-1 tile, multicast to both CTAs of the cluster
-            constexpr int HR = tfp::BN / CL;                 // rows per slice
-            constexpr int HB = tfp::B_BYTES / CL;            // bytes per slice
-            const uint16_t mask = uint16_t((1u << CL) - 1u);
-            if (act0)
-              tma_load_2d_mc(sa + tfp::A_BYTES + cta_rank * HB, &mapB, &full_bar[stage], k,
-                             b0 * tfp::BN + int(cta_rank) * HR, mask);
-            if (has1)
-              tma_load_2d_mc(sa + tfp::A_BYTES + tfp::B_BYTES + cta_rank * HB, &mapB, &full_bar[stage], k,
-                             b1 * tfp::BN + int(cta_rank) * HR, mask);
-          }
-          if (++stage == tfp::STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {   // ===== MMA issuer =====
-      // D = f32, A = B = f16 (format 0), both K-major
-      const uint32_t idesc = (1u << 4) | (uint32_t(tfp::BN >> 3) << 17) | (uint32_t(tfp::BM >> 4) << 24);
-      int stage = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      for (int b0 = blockIdx.y; b0 < nblk; b0 += 2 * S) {
-        const int b1 = b0 + S;
-        const bool has1 = b1 < nblk;
-        const int kend0 = min((b0 + 1) * tfp::BN, np);
-        const int kend = has1 ? min((b1 + 1) * tfp::BN, np) : kend0;
-        mbar_wait(&tempty_bar[0], acc_phase ^ 1);
-        if (has1) mbar_wait(&tempty_bar[1], acc_phase ^ 1);
-        tc_fence_after();
-        for (int k = 0; k < kend; k += tfp::BK) {
-          const bool act0 = k < kend0;
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = sbase + stage * tfp::STAGE_BYTES;
-          const uint64_t adesc = tfp::make_desc64(sa);
-          if (act0) {
-            const uint64_t bdesc = tfp::make_desc64(sa + tfp::A_BYTES);
-#pragma unroll
-            for (int kk = 0; kk < tfp::BK / tfp::UK; ++kk)
-              tc_mma_f16(tmem_base, adesc + uint64_t(kk * 2), bdesc + uint64_t(kk * 2), idesc, (k | kk) != 0 ? 1u : 0u);
-          }
-          if (has1) {
-            const uint64_t bdesc = tfp::make_desc64(sa + tfp::A_BYTES + tfp::B_BYTES);
-#pragma unroll
-            for (int kk = 0; kk < tfp::BK / tfp::UK; ++kk)
-              tc_mma_f16(tmem_base + uint32_t(tfp::BN), adesc + uint64_t(kk * 2), bdesc + uint64_t(kk * 2), idesc,
-                          (k | kk) != 0 ? 1u : 0u);
-          }
-          if (CL == 1) tc_commit(&empty_bar[stage]);
-          else tc_commit_mc(&empty_bar[stage], uint16_t((1u << CL) - 1u));   // frees the stage in BOTH CTAs
-          if (k + tfp::BK == kend0) tc_commit(&tfull_bar[0]);   // block b0 complete: drain it while b1 finishes
-          if (++stage == tfp::STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-        if (has1) tc_commit(&tfull_bar[1]);
-        acc_phase ^= 1;
-      }
-    }
-  } else {   // ===== epilogue (warps 2..5) =====
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
-    double tot0 = 0.0, tot1 = 0.0, tot2 = 0.0, tot3 = 0.0;
-    const double fac = panel_factor(hyp, d, lscale);
-    uint32_t acc_phase = 0;
-    for (int b0 = blockIdx.y; b0 < nblk; b0 += 2 * S) {
-#pragma unroll
-      for (int a = 0; a < 2; ++a) {
-        const int nb = b0 + a * S;
-        if (nb >= nblk) break;
-        mbar_wait(&tfull_bar[a], acc_phase);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(a * tfp::BN);
-        float part = 0.f;
-#pragma unroll 2
-        for (int c = 0; c < tfp::BN; c += 32) {
-          float v[32];
-          tmem_ld32(taddr + uint32_t(c), v);
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            s0 = fmaf(v[i], v[i], s0);
-            s1 = fmaf(v[i + 1], v[i + 1], s1);
-            s2 = fmaf(v[i + 2], v[i + 2], s2);
-            s3 = fmaf(v[i + 3], v[i + 3], s3);
-          }
-          part += (s0 + s1) + (s2 + s3);
-        }
-        const int slot = nb & 3;
-        const double dp = double(part) * fac;
-        if (slot == 0) tot0 += dp;
-        else if (slot == 1) tot1 += dp;
-        else if (slot == 2) tot2 += dp;
-        else tot3 += dp;
-        tc_fence_before();
-        mbar_arrive(&tempty_bar[a]);
-      }
-      acc_phase ^= 1;
-    }
-    const double tots[4] = {tot0, tot1, tot2, tot3};
-#pragma unroll
-    for (int g4 = 0; g4 < 4; ++g4)
-      if (g4 % S == int(blockIdx.y)) vpart[int64_t(g4) * qc_pad + c0 + row] = tots[g4];
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (CL > 1) {   // no CTA may exit while its peer can still multicast into it / arrive on its barriers
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-  }
-  if (warp == 2) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
-  }
-}
-
 // ------------------------------------------------------------------------------------------
 // 2-SM variant (tcgen05 cta_group::2): a CTA pair computes M = 256 candidates x N = 256 rows per
 // instruction.  Each CTA stages its own 128-candidate K* tile and only HALF (128 rows) of every
 // L^-1 tile; the tensor cores read the other half from the peer SM, so operand bytes ingested per
-// SM and per flop drop by a third versus k_vnorm_tf32_pair (that ingest, ~14 TB/s chip-wide, is
+// SM and per flop drop by a third versus the single-CTA form of round 1 (that ingest, ~14 TB/s chip-wide, is
 // what bounds the 1-SM kernels).  Stages are 3 x 8 KB = 24 KB, 8 stages.
 //   * both CTAs run a TMA producer; all loads signal the LEADER's full barrier (count 2, each
 //     producer arrives with its own expect_tx, the peer remotely through mapa)
@@ -416,7 +208,8 @@ k_vnorm_tf32_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 //     multicasts the "stage free" / "accumulator full" arrivals to both CTAs
 //   * each CTA's epilogue drains its own TMEM half and arrives on the leader's "accumulator empty"
 //     barrier (count 256)
-// Row-block pairing, triangular bounds and accumulation slots are those of k_vnorm_tf32_pair.
+// Two row blocks share every K* stage (both TMEM accumulators are live at once); block b only contracts
+// k < 256 (b + 1); partial sums go to fixed slots (bit-identical results for every split and chunking).
 // ------------------------------------------------------------------------------------------
 namespace tf2 {
 constexpr int BM = 128, BN = 256, BK = 32, UK = 16, STAGES = 8;   // BK binary16 values = 64-byte rows
@@ -2049,15 +1842,12 @@ static int launch_kstar(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
   return BBO_OK;
 }
 
-// *vpart_out / *nsplit_out: where the partial sums of this chunk are and how k_acq / k_acq_topk add them (4 = the
-// four fixed slots of `vpart`; -nblk = one slot per row block in the persistent panel's own buffer).
 // Does a chunk of qc_pad candidates run on the persistent form of the panel (launch_panel's own conditions)?
 static bool panel_persists(int64_t np, int64_t qc_pad, int reserve_sms) {
-  static const bool clus = getenv("BBO_TF32_NO_CLUSTER") == nullptr;
   static const bool no_persist = getenv("BBO_TF32_NO_PERSIST") != nullptr;
   static const int64_t l2_mb = getenv("BBO_TF32_PERSIST_MAX_MB") ? atoll(getenv("BBO_TF32_PERSIST_MAX_MB")) : 80;
   const int64_t tiles = qc_pad / tf::BM, nblk = ceil_div(np, tf::BN);
-  if (!clus || no_persist || tiles % 2 != 0) return false;
+  if (no_persist || tiles % 2 != 0) return false;
   const int ntp = int(tiles / 2), nrp = int((nblk + 1) / 2), nitems = ntp * nrp;
   const int pairs = (sm_count() - reserve_sms) / 2;
   const int nc = nitems < pairs ? nitems : pairs;
@@ -2066,30 +1856,27 @@ static bool panel_persists(int64_t np, int64_t qc_pad, int reserve_sms) {
          int64_t(nc) * maxj <= kSchedInts;
 }
 
+// *vpart_out / *nsplit_out: where the partial sums of this chunk are and how k_acq / k_acq_topk add them (4 = the
+// four fixed slots of `vpart`; -nblk = one slot per row block in the persistent panel's own buffer).
+// qc_pad is a multiple of 256 (ScoreWorkspace pads chunks so): every chunk runs on CTA pairs.
 // `reserve_sms`: SMs the persistent form leaves to the K* producer of the next chunk (0 = none).
 static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf32Scratch& t, int buf,
                         int64_t qc_pad, double* vpart, int* nsplit_out, double** vpart_out, cudaStream_t st,
                         int reserve_sms = 0) {
   const int64_t np = w.np;
-  // chunks with an even number of 128-candidate tiles run on CTA pairs (cta_group::2); BBO_TF32_NO_CLUSTER=1 sends
-  // every chunk through the single-CTA kernel that otherwise serves odd tile counts (same bits: tests compare them)
-  static const bool clus = getenv("BBO_TF32_NO_CLUSTER") == nullptr;
-  constexpr bool pair = true, two_sm = true;
+  if (qc_pad % (2 * tf::BM) != 0) return BBO_ERR_BAD_SHAPE;
+  constexpr bool two_sm = true;
   static DeviceOnce attr2_once;
   if (attr2_once.first()) {
-    BBO_CUDA_CHECK(cudaFuncSetAttribute(k_vnorm_tf32_pair<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        tfp::SMEM_BYTES));
     BBO_CUDA_CHECK(cudaFuncSetAttribute(k_vnorm_tf32_2sm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         tf2::SMEM_BYTES));
     BBO_CUDA_CHECK(cudaFuncSetAttribute(k_vnorm_tf32_2sm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         tf2::SMEM_BYTES));
   }
-  const bool use_cluster = pair && clus && (qc_pad / tf::BM) % 2 == 0;
   CUtensorMap mapA, mapB;
   int rc = make_map(&mapA, t.Ks[buf], qc_pad, np, tf::BM, tfp::BK);
   if (rc != BBO_OK) return rc;
-  rc = make_map(&mapB, reinterpret_cast<const __half*>(s.linv_tf32), tf32_rows(s.n), np,
-                use_cluster ? tf::BN / 2 : tf::BN, tfp::BK);
+  rc = make_map(&mapB, reinterpret_cast<const __half*>(s.linv_tf32), tf32_rows(s.n), np, tf::BN / 2, tfp::BK);
   if (rc != BBO_OK) return rc;
   const int64_t tiles = qc_pad / tf::BM;
   const int64_t nblk = ceil_div(np, tf::BN);
@@ -2104,11 +1891,11 @@ static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
   const int d_i = s.h.d;
   const float* lscale = linv_scale_ptr(s);
   prof_begin(kProfTf32, st);
-  if (use_cluster) {
+  {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(unsigned(tiles), unsigned(nsplit));
     cfg.blockDim = dim3(tf::THREADS);
-    cfg.dynamicSmemBytes = two_sm ? tf2::SMEM_BYTES : tfp::SMEM_BYTES;
+    cfg.dynamicSmemBytes = tf2::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -2180,9 +1967,7 @@ static int launch_panel(const bbo_gp_state& s, const ScoreWorkspace& w, const Tf
     } else
       BBO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_vnorm_tf32_2sm<false>, mapA, mapB, np_i, qp_i, vp, shrink,
                                         static_cast<const int*>(nullptr), 0, hyp, d_i, lscale));
-  } else
-    k_vnorm_tf32_pair<1><<<dim3(unsigned(tiles), unsigned(nsplit)), tf::THREADS, tfp::SMEM_BYTES, st>>>(
-        mapA, mapB, int(np), w.qp, vpart, hyp, d_i, lscale);
+  }
   BBO_LAUNCH_CHECK();
   prof_end(kProfTf32, st);
   return BBO_OK;
@@ -2274,12 +2059,12 @@ int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const vo
   auto side_for = [&](int64_t i) -> int {   // SMs reserved while panel(i) and K*(i+1) run
     if (kstar_sms < 2 || !two_streams || !use_kstar_umma(d)) return 0;
     const int64_t qc = chunk_len(i);
-    return panel_persists(w.np, ceil_div(qc, 128) * 128, kstar_sms) ? kstar_sms : 0;
+    return panel_persists(w.np, ceil_div(qc, 256) * 256, kstar_sms) ? kstar_sms : 0;
   };
   {
     const int64_t qc = chunk_len(0);
     mark(aux->sk);
-    rc = launch_kstar(s, w, t, 0, chunk_ptr(0), xq_is_f32, qc, ceil_div(qc, 128) * 128, t.mu[0], aux->sk);
+    rc = launch_kstar(s, w, t, 0, chunk_ptr(0), xq_is_f32, qc, ceil_div(qc, 256) * 256, t.mu[0], aux->sk);
     if (rc != BBO_OK) return rc;
     mark(aux->sk);
     if (two_streams) BBO_CUDA_CHECK(cudaEventRecord(aux->kdone[0], aux->sk));
@@ -2298,7 +2083,7 @@ int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const vo
       if (two_streams && i >= 2) BBO_CUDA_CHECK(cudaStreamWaitEvent(aux->sk, aux->sdone[buf], 0));
       const int64_t qn = chunk_len(i + 1);
       mark(aux->sk);
-      rc = launch_kstar(s, w, t, nb, chunk_ptr(i + 1), xq_is_f32, qn, ceil_div(qn, 128) * 128, t.mu[(i + 1) % 3],
+      rc = launch_kstar(s, w, t, nb, chunk_ptr(i + 1), xq_is_f32, qn, ceil_div(qn, 256) * 256, t.mu[(i + 1) % 3],
                         aux->sk, side_for(i));
       if (rc != BBO_OK) return rc;
       mark(aux->sk);
@@ -2313,7 +2098,7 @@ int score_tf32_pipeline(const bbo_gp_state& s, const ScoreWorkspace& w, const vo
     int nsplit = 1;
     double* vpart = nullptr;
     mark(st);
-    rc = launch_panel(s, w, t, buf, ceil_div(qc, 128) * 128, w.vpart + int64_t(buf) * 4 * w.qp, &nsplit, &vpart, st,
+    rc = launch_panel(s, w, t, buf, ceil_div(qc, 256) * 256, w.vpart + int64_t(buf) * 4 * w.qp, &nsplit, &vpart, st,
                       i + 1 < nchunk ? side_for(i) : 0);
     if (rc != BBO_OK) return rc;
     mark(st);
