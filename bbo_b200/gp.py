@@ -43,7 +43,7 @@ def _check_2d(name: str, value):
         raise ValueError(f"Expected 2D Tensor, got {value.dim()}D Tensor")
 
 
-_KS_BUDGET_MB = int(os.environ.get("BBO_TF32_KS_BUDGET_MB", "768"))   # K* bytes per TF32 chunk
+_KS_BUDGET_MB = int(os.environ.get("BBO_TF32_KS_BUDGET_MB", "384"))   # K* bytes (binary16) per tensor-core chunk
 
 
 def default_q_chunk(n: int, budget_bytes: int = 512 << 20) -> int:
@@ -466,7 +466,7 @@ class CudaGP(Surrogate):
             qc = min(self._q_chunk, max(128, (q + 127) // 128 * 128))
             wave = self._sm_count * 128      # one 128-candidate tile per SM and per wave
             if prec != _lib.PREC_FP64 and q >= wave and self._q_chunk_auto:
-                qc = min(q // wave, max(1, (_KS_BUDGET_MB << 20) // (wave * self.np * 4))) * wave
+                qc = min(q // wave, max(1, (_KS_BUDGET_MB << 20) // (wave * self.np * 2))) * wave
             self._score_shape = (qc, prec)
             ws = self._workspace("score%d" % prec,
                                  int(self._lib.bbo_gp_score_workspace_bytes(self.n, self.d, qc, prec)))
