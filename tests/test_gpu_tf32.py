@@ -31,6 +31,7 @@ TOL = 1e-3
     (1500, 24, 9000, O.RBF),        # six 256-row blocks, the last one partial
     (2040, 13, 70000, O.MATERN52),  # np = 2048, several work-list items per CTA pair
     (640, 8, 3000, O.RBF),          # one operand box, three 256-row blocks (last partial)
+    (120, 28, 60000, O.RBF),        # one 128-observation block, several candidate tiles per K* CTA (A-tile ring)
 ])
 def test_tf32_posterior_and_selection(n, d, q, kind, cuda_device):
     import bbo_b200 as B
