@@ -1059,19 +1059,55 @@ k_refine_acq(bbo_gp_hyper h, bbo_acq a, const double* __restrict__ hyp, const do
     }
     __syncthreads();
   }
-  if (c == 0) {
-    info[2] = red[0];
-    info[3] = double(cnt[0]);
-  }
+  if (c == 0) info[3] = double(cnt[0]);     // (the error entries are k_refine_info's)
 }
 
-__global__ void k_refine_info(const double* __restrict__ topk_s, int k, const double* __restrict__ sh_s,
-                              const int64_t* __restrict__ sh_i, int m, const double* __restrict__ bound,
-                              double* __restrict__ info) {
-  info[0] = topk_s[k - 1];
-  double b = *bound;
-  if (sh_i[m - 1] >= 0) b = fmax(b, sh_s[m - 1]);   // full short-list: whatever it displaced scored <= its last entry
-  info[1] = b;
+// Evidence (see bbo_gp_refine_info).  The observed TF32 score error is taken over the short-listed candidates that
+// did NOT make the returned k -- the ones nearest the cut: for EI / PI a score error scales with the score, and the
+// largest scores of the list (orders of magnitude above the k-th one in a large pool) say nothing about candidates
+// at the cut.  info[4] keeps the maximum over the whole list.
+__global__ void __launch_bounds__(kRefineRows)
+k_refine_info(const double* __restrict__ topk_s, int k, const double* __restrict__ sh_s,
+              const int64_t* __restrict__ sh_i, int m, const double* __restrict__ bound,
+              const double* __restrict__ f64_s, const int64_t* __restrict__ f64_i, const double* __restrict__ tf_s,
+              double* __restrict__ info) {
+  __shared__ double red_all[kRefineRows], red_cut[kRefineRows];
+  __shared__ int cnt_cut[kRefineRows];
+  const int c = threadIdx.x;
+  const double kth = topk_s[k - 1];
+  double e_all = 0.0, e_cut = 0.0;
+  int n_cut = 0;
+  if (c < m && f64_i[c] >= 0) {
+    const double e = fabs(f64_s[c] - tf_s[c]);
+    if (e == e && e < INFINITY) {
+      e_all = e;
+      if (f64_s[c] < kth) {
+        e_cut = e;
+        n_cut = 1;
+      }
+    }
+  }
+  red_all[c] = e_all;
+  red_cut[c] = e_cut;
+  cnt_cut[c] = n_cut;
+  __syncthreads();
+  for (int o = kRefineRows / 2; o > 0; o >>= 1) {
+    if (c < o) {
+      red_all[c] = fmax(red_all[c], red_all[c + o]);
+      red_cut[c] = fmax(red_cut[c], red_cut[c + o]);
+      cnt_cut[c] += cnt_cut[c + o];
+    }
+    __syncthreads();
+  }
+  if (c == 0) {
+    info[0] = kth;
+    double b = *bound;
+    if (sh_i[m - 1] >= 0) b = fmax(b, sh_s[m - 1]);   // full short-list: whatever it displaced scored <= its last entry
+    info[1] = b;
+    info[2] = cnt_cut[0] > 0 ? red_cut[0] : red_all[0];
+    info[4] = red_all[0];
+    info[5] = double(cnt_cut[0]);
+  }
 }
 
 static DeviceOnce g_attr_once;
@@ -1169,7 +1205,8 @@ static int refine_rescore(const bbo_gp_state& s, const bbo_acq& acq, const Score
   BBO_LAUNCH_CHECK();
   k_topk_seg<<<1, 256, 0, st>>>(r.la_s, r.la_i, 0, int64_t(k) + m, k, topk_s, topk_i);
   BBO_LAUNCH_CHECK();
-  k_refine_info<<<1, 1, 0, st>>>(topk_s, k, r.sh_s, r.sh_i, m, r.bound, r.info);
+  k_refine_info<<<1, kRefineRows, 0, st>>>(topk_s, k, r.sh_s, r.sh_i, m, r.bound, r.la_s + k, r.la_i + k, r.tf_s,
+                                           r.info);
   BBO_LAUNCH_CHECK();
   prof_end(kProfSelect, st);
   return BBO_OK;
@@ -1181,7 +1218,7 @@ int refine_info(const void* ws, size_t ws_bytes, int64_t n, int64_t d, int64_t q
   int rc = w.bind(const_cast<void*>(ws), ws_bytes, n, d, q_chunk, BBO_PREC_TF32_REFINE, false);
   if (rc != BBO_OK) return rc;
   const RefineScratch r = carve_refine(w.refine, w.np, d);
-  BBO_CUDA_CHECK(cudaMemcpyAsync(info_host, r.info, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  BBO_CUDA_CHECK(cudaMemcpyAsync(info_host, r.info, 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
   BBO_CUDA_CHECK(cudaStreamSynchronize(st));
   return BBO_OK;
 }

@@ -510,18 +510,21 @@ class CudaGP(Surrogate):
         """Evidence of the last ``precision="tf32+refine"`` call (``bbo_gp_refine_info``; synchronises):
         ``kth_score`` the k-th best float64 score returned, ``unscored_bound`` an upper bound of the TF32 score of
         every candidate that was not re-scored, ``tf32_error`` the largest |TF32 - float64| score difference seen on
-        the short-list, ``shortlist`` its size, and ``certified`` = the margin kth_score - unscored_bound exceeds
+        the ``at_the_cut`` short-listed candidates that did not make the top k (for EI / PI the error scales with
+        the score: the top of the list says nothing about the cut; ``tf32_error_whole_list`` is the maximum over
+        all of them), ``shortlist`` its size, and ``certified`` = the margin kth_score - unscored_bound exceeds
         ``factor`` x tf32_error (or nothing was left unscored): no unscored candidate can belong to the float64
         top-k, i.e. the selection equals the ``precision="fp64"`` selection."""
         qc, prec = getattr(self, "_score_shape", (None, None))
         if prec != _lib.PREC_TF32_REFINE:
             raise RuntimeError("no tf32+refine call has been made")
         ws = self._ws["score%d" % prec]
-        info = (C.c_double * 4)()
+        info = (C.c_double * 6)()
         with torch.cuda.device(self._device):
             _lib.check(self._lib.bbo_gp_refine_info(_lib.ptr(ws), ws.numel(), self.n, self.d, qc, info,
                                                     _lib.stream_ptr(self._device)), "bbo_gp_refine_info")
-        kth, bound, err, cnt = (float(v) for v in info)
+        kth, bound, err, cnt, err_all, ncut = (float(v) for v in info)
         margin = kth - bound
-        return {"kth_score": kth, "unscored_bound": bound, "tf32_error": err, "shortlist": int(cnt),
-                "margin": margin, "certified": bool(bound == float("-inf") or margin > factor * err)}
+        return {"kth_score": kth, "unscored_bound": bound, "tf32_error": err, "tf32_error_whole_list": err_all,
+                "at_the_cut": int(ncut), "shortlist": int(cnt), "margin": margin,
+                "certified": bool(bound == float("-inf") or margin > factor * err)}

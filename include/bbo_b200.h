@@ -272,13 +272,17 @@ int bbo_gp_score_pool(const bbo_gp_state* st, const bbo_acq* acq, int32_t precis
 /* BBO_PREC_TF32_REFINE: size of the short-list kept by the TF32 pass (max(64, 8k), at most 256).        */
 int32_t bbo_refine_shortlist(int32_t k);
 /* Evidence of the last BBO_PREC_TF32_REFINE call that used this workspace (same n, d, q_chunk as that call);
- * synchronises `stream`.  info_host[4]:
+ * synchronises `stream`.  info_host[6]:
  *   [0] k-th best float64 score returned
  *   [1] upper bound of the TF32 score of every candidate that was NOT re-scored (-inf if all were)
- *   [2] max |TF32 score - float64 score| over the short-list (the observed TF32 score error)
+ *   [2] observed TF32 score error AT THE CUT: max |TF32 score - float64 score| over the short-listed candidates
+ *       that did not make the returned k (for EI / PI a score error scales with the score, so the top of the list
+ *       says nothing about candidates at the cut); [4] when no such candidate exists
  *   [3] number of short-listed candidates
- * The selection provably equals the float64 mode's if no unscored candidate's float64 score can reach [0],
- * i.e. if [0] - [1] exceeds the TF32 score error; callers compare it with a multiple of [2].              */
+ *   [4] max |TF32 score - float64 score| over the whole short-list
+ *   [5] number of candidates behind [2]
+ * The selection equals the float64 mode's if no unscored candidate's float64 score can reach [0], i.e. if
+ * [0] - [1] exceeds the TF32 score error of the candidates at the cut; callers compare it with a multiple of [2]. */
 int bbo_gp_refine_info(const void* workspace_dev, size_t workspace_bytes, int64_t n, int64_t d, int64_t q_chunk,
                        double* info_host, void* stream);
 
