@@ -1466,6 +1466,7 @@ __global__ void k_linv_scale(float* __restrict__ sc) {
     int ex;
     frexpf(m, &ex);          // m = f 2^ex, f in [0.5, 1)
     e = 14 - ex;             // 2^e m in [2^13, 2^14)
+    e = e > 50 ? 50 : (e < -50 ? -50 : e);   // keep 2^-2e a normal float (|L^-1| beyond 2^+-36 is not a GP)
   }
   sc[0] = exp2f(float(-2 * e));
   sc[1] = exp2f(float(e));
