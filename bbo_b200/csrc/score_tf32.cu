@@ -1078,13 +1078,13 @@ constexpr int OUT_BYTES = 2 * OUT_TILE;            // two per epilogue warp: the
 constexpr int kMaxD = 30;                          // two A tiles resident (the next one loads under this one's MMAs)
 constexpr int kMaxDStream = 126;                   // dk = 8 ceil((d+2)/8) <= 128
 // Shared-memory plan for `nbox` boxes per operand row: A tiles (two when they fit), ring of B boxes, staging tiles
-// (two per epilogue warp when they fit).  216 KB of dynamic shared memory + 1 KB alignment slack + 7.5 KB static.
+// (two per epilogue warp when they fit).  214 KB of dynamic shared memory + 1 KB alignment slack + 11.5 KB static.
 struct Plan {
   int na, ring, stg2;
   size_t bytes;
 };
 static Plan plan(int nbox) {
-  const int budget = 216 * 1024;
+  const int budget = 214 * 1024;
   Plan p;
   p.na = (2 * nbox * BOX_BYTES + 4 * BOX_BYTES + EPI_WARPS * OUT_BYTES <= budget) ? 2 : 1;
   p.stg2 = (p.na * nbox * BOX_BYTES + 4 * BOX_BYTES + EPI_WARPS * OUT_BYTES <= budget) ? 1 : 0;
@@ -1187,7 +1187,7 @@ k_kstar_umma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       t_empty[ku::ACCS];
   __shared__ uint32_t tmem_base_sh;
   __shared__ float mu_sh[2][3][ku::BM];
-  __shared__ __align__(16) float al_sh[ku::EPI_WARPS][2][32];
+  __shared__ __align__(16) float al_sh[ku::EPI_WARPS][2][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -1207,7 +1207,7 @@ k_kstar_umma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     }
     for (int a = 0; a < ku::ACCS; ++a) {
       mbar_init(&t_full[a], 1);
-      mbar_init(&t_empty[a], ku::EPI_WARPS * 32);
+      mbar_init(&t_empty[a], ku::EPI_WARPS * 32 / 2);   // one group of eight epilogue warps drains an accumulator
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1317,23 +1317,27 @@ k_kstar_umma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       }
     }
   } else {   // ===== epilogue (warps 2..17) =====
-    // warp = (TMEM lane quarter, 32-column slab): 16 warps, four per scheduler, so that one warp's TMEM load, MUFU
-    // and TMA-store latencies are covered by the other three
-    const int ew = warp - 2, quarter = warp & 3, colq = ew >> 2;
+    // Two groups of eight warps take ALTERNATE 128 x 128 blocks (group g the blocks with blk % 2 == g, i.e. the
+    // accumulators g and g + 2 of the ring); inside a block a warp owns one TMEM lane quarter and 64 columns (two
+    // 32-column slabs).  While one group waits for its accumulator, loads it and hands its slabs to the TMA store, the
+    // other is in its MUFU phase: with all sixteen warps on the same block the XU pipe idled through every load /
+    // store phase (57 % busy).
+    const int ew = warp - 2, quarter = warp & 3, grp = (ew >> 2) & 1, half = ew >> 3;
     const int row = quarter * 32 + lane;
-    const uint32_t stg = sbase + uint32_t(stg_off + ew * (stg2 ? ku::OUT_BYTES : ku::OUT_TILE));
+    const int stg_bytes = stg2 ? ku::OUT_BYTES : ku::OUT_TILE;
+    const uint32_t stg = sbase + uint32_t(stg_off + ew * stg_bytes);
     const float s2 = float(hyp[2 * d]);
     const float kLog2e = 1.4426950408889634f;
     const double cmean = hyp[2 * d + 1];
-    const uint32_t tlane = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(colq * 32);
-    const float* abase = alpha32 + colq * 32;
+    const uint32_t tlane = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(half * 64);
+    const float* abase = alpha32 + half * 64;
+    const int part = 2 * grp + half;           // which of the four partial sums of mu this warp carries
     float m = 0.f;
-    // alpha of this warp's 32 columns, one block ahead (cp.async, per-warp double buffer): the values are used
-    // once per tile, so they always come from L2
+    // alpha of this warp's 64 columns, one own block ahead (cp.async, per-warp double buffer)
     float* alw = &al_sh[ew][0][0];
     auto alpha_fetch = [&](int nb_, int buf_) {
-      if (lane < 8) {
-        const unsigned sa = smem_u32(alw + buf_ * 32 + lane * 4);
+      if (lane < 16) {
+        const unsigned sa = smem_u32(alw + buf_ * 64 + lane * 4);
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(abase + nb_ * ku::BN + lane * 4)
                      : "memory");
       }
@@ -1341,79 +1345,85 @@ k_kstar_umma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     };
     const int my_tiles = (tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
     const int nblocks = my_tiles * nblk;     // 128 x 128 blocks this CTA produces, accumulators in ring order
-    uint32_t acc_phase = 0;
-    int acc = 0;
-    if (nblocks > 0) alpha_fetch(0, 0);
-    int tile = blockIdx.x, nb = 0, tcount = 0;
-    for (int blk = 0; blk < nblocks; ++blk) {
-      const int nb_next = (nb + 1 == nblk) ? 0 : nb + 1;
-      const float* al = alw + (blk & 1) * 32;
-      alpha_fetch(nb_next, (blk + 1) & 1);                       // next block's alpha (harmless after the last)
-      uint32_t r[32];
-      mbar_wait(&t_full[acc], acc_phase);
-      tc_fence_after();
-      tmem_ld32_issue(tlane + uint32_t(acc * ku::BN), r);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");      // this block's alpha has landed
-      if (lane == 0) {   // the staging tile about to be written is free again
-        if (stg2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      }
-      __syncwarp();
-      tmem_ld_wait(r);
-      tc_fence_before();
-      mbar_arrive(&t_empty[acc]);
-      if (++acc == ku::ACCS) {
-        acc = 0;
-        acc_phase ^= 1;
-      }
-      // values -> correlations, mu partial, binary16 pairs into the 64-byte-swizzled staging tile, TMA store
-      const uint32_t stile = stg + uint32_t(stg2 ? (blk & 1) * ku::OUT_TILE : 0);
-      const uint32_t sdst = stile + uint32_t(lane * 64);
-#pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {
-        uint32_t u[4];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float4 av = *reinterpret_cast<const float4*>(al + c8 * 8 + h * 4);
-          const float a4[4] = {av.x, av.y, av.z, av.w};
-          float cv[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float x = __uint_as_float(r[c8 * 8 + h * 4 + e]);
-            if (!MATERN) {
-              cv[e] = ex2_approx(fminf(x, 0.f));
-            } else {
-              const float rr = 2.2360679775f * sqrtf(fmaxf(x, 0.f));
-              cv[e] = fmaf(rr, fmaf(rr, 1.f / 3.f, 1.f), 1.f) * ex2_approx(-kLog2e * rr);
-            }
-            m = fmaf(cv[e], a4[e], m);
-          }
-          u[2 * h] = pack_half2(cv[0], cv[1]);
-          u[2 * h + 1] = pack_half2(cv[2], cv[3]);
+    if (grp < nblocks) alpha_fetch(grp % nblk, 0);          // block index grp is this group's first
+    int mine = 0;                                           // own blocks done: parity selects the alpha buffer
+    int tile = blockIdx.x, tcount = 0;
+    for (int blk0 = 0; blk0 < nblocks; blk0 += nblk) {      // one candidate tile
+      for (int nb = 0; nb < nblk; ++nb) {
+        const int blk = blk0 + nb;
+        if ((blk & 1) != grp) continue;
+        const int acc = blk & 3;
+        const uint32_t acc_phase = uint32_t(blk >> 2) & 1u;
+        const float* al = alw + (mine & 1) * 64;
+        {
+          const int nxt = blk + 2;                           // this group's next block (harmless after the last)
+          alpha_fetch(nxt < nblocks ? nxt % nblk : 0, (mine + 1) & 1);
         }
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdst + uint32_t((c8 ^ ((lane >> 1) & 3)) * 16)),
-                     "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3])
-                     : "memory");
+        mbar_wait(&t_full[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          uint32_t r[32];
+          tmem_ld32_issue(tlane + uint32_t(acc * ku::BN + sl * 32), r);
+          if (sl == 0) asm volatile("cp.async.wait_group 1;" ::: "memory");      // this block's alpha has landed
+          if (lane == 0) {   // the staging tile about to be written is free again
+            if (stg2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
+          __syncwarp();
+          tmem_ld_wait(r);
+          if (sl == 1) {                                     // both slabs are in registers: the accumulator is free
+            tc_fence_before();
+            mbar_arrive(&t_empty[acc]);
+          }
+          // values -> correlations, mu partial, binary16 pairs into the 64-byte-swizzled staging tile, TMA store
+          const uint32_t stile = stg + uint32_t(stg2 ? sl * ku::OUT_TILE : 0);
+          const uint32_t sdst = stile + uint32_t(lane * 64);
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8) {
+            uint32_t u[4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const float4 av = *reinterpret_cast<const float4*>(al + sl * 32 + c8 * 8 + h * 4);
+              const float a4[4] = {av.x, av.y, av.z, av.w};
+              float cv[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float x = __uint_as_float(r[c8 * 8 + h * 4 + e]);
+                if (!MATERN) {
+                  cv[e] = ex2_approx(fminf(x, 0.f));
+                } else {
+                  const float rr = 2.2360679775f * sqrtf(fmaxf(x, 0.f));
+                  cv[e] = fmaf(rr, fmaf(rr, 1.f / 3.f, 1.f), 1.f) * ex2_approx(-kLog2e * rr);
+                }
+                m = fmaf(cv[e], a4[e], m);
+              }
+              u[2 * h] = pack_half2(cv[0], cv[1]);
+              u[2 * h + 1] = pack_half2(cv[2], cv[3]);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdst + uint32_t((c8 ^ ((lane >> 1) & 3)) * 16)),
+                         "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3])
+                         : "memory");
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();                          // staging tile complete
+          if (lane == 0) {
+            ku::tma_store_2d(&mapO, stile, nb * ku::BN + half * 64 + sl * 32, tile * ku::BM + quarter * 32);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        ++mine;
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();                          // staging tile complete; all lanes are done with al
-      if (lane == 0) {
-        ku::tma_store_2d(&mapO, stile, nb * ku::BN + colq * 32, tile * ku::BM + quarter * 32);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
-      if (nb_next == 0) {
-        // mu = c + the four column slabs in a fixed order
-        if (colq > 0) mu_sh[tcount & 1][colq - 1][row] = m;
-        asm volatile("bar.sync 1, %0;" ::"n"(ku::EPI_WARPS * 32) : "memory");
-        if (colq == 0)
-          mu[int64_t(tile) * ku::BM + row] =
-              cmean + double(s2) * double(((m + mu_sh[tcount & 1][0][row]) + mu_sh[tcount & 1][1][row]) +
-                                          mu_sh[tcount & 1][2][row]);
-        m = 0.f;
-        tile += gridDim.x;
-        ++tcount;
-      }
-      nb = nb_next;
+      // end of the tile: mu = c + s2 x the four partial sums (group, column half) in a fixed order
+      if (part > 0) mu_sh[tcount & 1][part - 1][row] = m;
+      asm volatile("bar.sync 1, %0;" ::"n"(ku::EPI_WARPS * 32) : "memory");
+      if (part == 0)
+        mu[int64_t(tile) * ku::BM + row] =
+            cmean + double(s2) * double(((m + mu_sh[tcount & 1][0][row]) + mu_sh[tcount & 1][1][row]) +
+                                        mu_sh[tcount & 1][2][row]);
+      m = 0.f;
+      tile += gridDim.x;
+      ++tcount;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
