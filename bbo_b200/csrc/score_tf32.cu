@@ -1057,7 +1057,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 //              128 x 128 block, fully unrolled on the template parameter DKS = dk / 8 (every descriptor = base +
 //              constant; with run-time bounds this thread was the bottleneck); four 128-column TMEM accumulators in a
 //              ring, so the tensor core runs up to four blocks ahead of the epilogue
-//   warps 2-17 epilogue, one (TMEM lane quarter, 32-column slab) per warp: tcgen05.ld 32 lanes x 32 columns ->
+//   warps 2-17 epilogue, two groups of eight warps on alternate blocks (accumulators), a warp = one TMEM lane quarter
+//              x 64 columns of its block, slab by slab: tcgen05.ld 32 lanes x 32 columns ->
 //              ex2 (Matern: sqrt, cubic, ex2) -> mu += K* alpha (alpha staged one block ahead by cp.async) ->
 //              cvt.rn.f16x2.f32 -> st.shared.v4 into one of two 64-byte-swizzled 32 x 32 staging tiles ->
 //              TMA tensor store (cp.async.bulk.tensor ... bulk_group)
