@@ -1332,7 +1332,6 @@ k_kstar_umma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const double cmean = hyp[2 * d + 1];
     const uint32_t tlane = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(half * 64);
     const float* abase = alpha32 + half * 64;
-    const int part = 2 * grp + half;           // which of the four partial sums of mu this warp carries
     float m = 0.f;
     // alpha of this warp's 64 columns, one own block ahead (cp.async, per-warp double buffer)
     float* alw = &al_sh[ew][0][0];
@@ -1415,7 +1414,11 @@ k_kstar_umma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         }
         ++mine;
       }
-      // end of the tile: mu = c + s2 x the four partial sums (group, column half) in a fixed order
+      // end of the tile: mu = c + s2 x four partial sums in a fixed order.  A partial is keyed by the PARITY of the
+      // block index inside the tile (and the column half), not by the group: which group gets the even blocks of a
+      // tile depends on the tile's position in this CTA's sequence when nblk is odd, and mu must not depend on that
+      // (bit-identical results for every chunking and sharding).
+      const int part = 2 * (grp ^ (blk0 & 1)) + half;
       if (part > 0) mu_sh[tcount & 1][part - 1][row] = m;
       asm volatile("bar.sync 1, %0;" ::"n"(ku::EPI_WARPS * 32) : "memory");
       if (part == 0)
