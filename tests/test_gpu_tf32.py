@@ -163,3 +163,29 @@ print("RESULT" + json.dumps(out))
         for other in ("rounds", "side"):
             so, io = res[other][key]
             assert io == iu and so == su, other
+
+
+@pytest.mark.parametrize("n,d", [(600, 20), (1024, 12), (130, 40)])
+def test_tf32_results_do_not_depend_on_the_chunking(n, d, cuda_device):
+    """Every candidate's mu, variance and score carry the same BITS whatever chunk, CTA and tile position it is
+    processed in (the multi-GPU path and the host-pool path rely on it: a shard boundary or a staging buffer only
+    moves chunk boundaries).  n = 600 has an odd number of 128-observation blocks (5), where the K* producer's two
+    epilogue groups swap roles from one candidate tile to the next."""
+    import bbo_b200 as B
+    p, X, y = synth_problem(5 + n, n, d, kind=O.RBF, noise=1e-3, ls_mean=0.0)
+    pool = torch.as_tensor(np.random.default_rng(n).random((45000, d))).cuda()
+    acq = B.UCB()
+    ref = None
+    for qc in (None, 8192, 12160, 45056):
+        gp = gp_from_params(p, X, y, **({} if qc is None else {"q_chunk": qc}))
+        out = gp.score_pool(pool, acq, 8, precision="tf32", return_all=True)
+        if ref is None:
+            ref = out
+            continue
+        for a, b in zip(out, ref):
+            assert torch.equal(a, b)
+    # a shifted shard: the same candidates at other positions of other chunks
+    gp = gp_from_params(p, X, y, q_chunk=8192)
+    _, _, mu, var, sc = gp.score_pool(pool[1000:31000], acq, 8, precision="tf32", return_all=True)
+    assert torch.equal(mu, ref[2][1000:31000]) and torch.equal(var, ref[3][1000:31000])
+    assert torch.equal(sc, ref[4][1000:31000])
