@@ -601,7 +601,7 @@ __global__ void k_panel_schedule(int ntp, int nrp, int nc, int gs, int maxj, int
 }
 
 // ------------------------------------------------------------------------------------------
-// K* (qc_pad, np) float32 (TF32-rounded) and mu.  grid (qc_pad/64), 256 threads.
+// K* (qc_pad, np) binary16 correlations and mu (CUDA cores, any d).  grid (qc_pad/64), 256 threads.
 // ------------------------------------------------------------------------------------------
 constexpr int kFC = 32, kFS = kFC + 1;
 
@@ -1452,14 +1452,14 @@ static size_t kstar_fast_smem(int d) {
   return sizeof(float) * (size_t(128) * LS + 2 * 64 * LS + 128 + 128 + 128);
 }
 
-// out (rows256, np): TF32-rounded copy of linv (np, np); rows >= np are zero so that every 256-row TMA box of the
+// out (rows256, np): the panel's copy of linv (np, np); rows >= np are zero so that every 256-row TMA box of the
 // B operand is fully in bounds.  Inside each 256-row block the rows are stored in REVERSE order (physical row c holds
 // logical row 255 - c).  The panel only sums squares over the rows of a block, so their order is free, and this order
 // puts the rows that are structurally zero in the diagonal block (logical row < column) at the END: for the
-// 16-column stage starting kk columns into the diagonal block only the first 256 - kk physical rows are non-zero and
+// 32-column stage starting kk columns into the diagonal block only the first 256 - kk physical rows are non-zero and
 // the tensor core is given N = 256 - kk instead of 256 (k_vnorm_tf32_2sm: accumulator column c = physical row c in
 // every stage).
-// binary16 copy of L^-1 for the panel: out[prow, col] = half(2^e linv[lrow, col]) with the rows of every 256-row block
+// Values: binary16 copy of L^-1: out[prow, col] = half(2^e linv[lrow, col]) with the rows of every 256-row block
 // in reverse order (see the panel's diagonal blocks), zero rows up to tf32_rows(n), and e chosen so that the largest
 // |entry| lands in [2^13, 2^14): the 10-bit mantissa is TF32's, the scaling keeps every entry that matters in the
 // normal range (an entry below 2^-28 of the largest is rounded with an absolute error of 2^-39 of the largest).
