@@ -82,3 +82,40 @@ def test_product_code_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("the oracle", ""), f"{f} mentions oracle"
+
+
+def test_header_is_plain_c_and_a_c_program_links(tmp_path):
+    """include/bbo_b200.h is the contract a non-Python host binds (cgo / JNI / plain C): it must compile as strict C99
+    and a C program must link against the shared library and call the GPU-free entry points."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    from bbo_b200 import _lib
+    src = tmp_path / "consumer.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "bbo_b200.h"
+int main(void) {
+  bbo_gp_hyper h;
+  bbo_acq a;
+  h.kind = BBO_KERNEL_RBF; h.d = 3; h.pairwise_eps = 0.0; h.noise = 1e-6;
+  a.kind = BBO_ACQ_EI;
+  (void)a;
+  /* null pointers: validation must refuse before touching the device */
+  int rc = bbo_gp_fit_value_grad(&h, 10, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+  printf("%d %lld %lld %d %d\n", (int)bbo_version(), (long long)bbo_padded_n(129),
+         (long long)bbo_tf32_rows(300), rc, (int)bbo_refine_shortlist(8));
+  return 0;
+}
+''')
+    exe = tmp_path / "consumer"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+           str(src), "-o", str(exe), "-L", libdir, "-lbbo_b200", "-Wl,-rpath," + libdir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    ver, pad, rows, rc, m = out.stdout.split()
+    assert int(ver) >= 100 and int(pad) == 256 and int(rows) == 512 and int(rc) == 2 and int(m) == 64
