@@ -43,7 +43,7 @@ def _check_2d(name: str, value):
         raise ValueError(f"Expected 2D Tensor, got {value.dim()}D Tensor")
 
 
-_KS_BUDGET_MB = int(os.environ.get("BBO_TF32_KS_BUDGET_MB", "384"))   # K* bytes (binary16) per tensor-core chunk
+_KS_BUDGET_MB = int(os.environ.get("BBO_TF32_KS_BUDGET_MB", "768"))   # K* bytes (binary16) per tensor-core chunk
 
 
 def default_q_chunk(n: int, budget_bytes: int = 512 << 20) -> int:
