@@ -1,7 +1,8 @@
 """n-sweep of the scoring pass on one B200: candidates/s and the tensor-roofline fraction of the WHOLE step for
-n in {256 ... 8192} at d=20 (ARD RBF, l=0.5, noise=1e-4, EI, top-8), in the headline mode (tf32+refine), plain TF32
-and float64.  One JSON line per n (profiles/n_sweep_r02.jsonl).  The roofline ceiling of a step is
-peak_tf32 / (n^2 + 3nd + 4n) candidates/s with peak_tf32 from profiles/measured_peaks_tf32_f64.json (sustained)."""
+n in {256 ... 8192} at d=20 (ARD RBF, l=0.5, noise=1e-4, EI, top-8), in the headline mode (tf32+refine), the plain
+tensor-core mode and float64.  One JSON line per n (profiles/n_sweep_r02.jsonl).  The roofline ceiling of a step is
+peak / (n^2 + 3nd + 4n) candidates/s with peak = the sustained dense bf16 GEMM rate (the panel multiplies 16-bit
+operands: MEASURED_PEAKS.json, else profiles/measured_peaks_tf32_f64.json) resp. the stored cuBLAS f64 rate."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -12,6 +13,10 @@ from bbo_b200.pool import uniform_pool
 
 D = 20
 peaks = json.load(open(os.path.join(ROOT, "profiles", "measured_peaks_tf32_f64.json")))
+try:
+    peaks["bf16_tflops_sustained"] = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]
+except Exception:  # noqa: BLE001
+    pass
 
 
 def ev(fn, reps=3, warm=2):
@@ -51,9 +56,9 @@ for n in [int(v) for v in (sys.argv[1:] or [256, 512, 768, 1024, 1536, 2048, 307
             rate = q / ms * 1e3
         key = prec.replace("+", "_")
         row[key + "_cand_per_s"] = rate
-        peak = peaks["f64_tflops"] if prec == "fp64" else peaks["tf32_tflops_sustained"]
+        peak = peaks["f64_tflops"] if prec == "fp64" else peaks["bf16_tflops_sustained"]
         row[key + "_tflops"] = rate * flop / 1e12
-        row[key + "_frac_of_" + ("f64_peak" if prec == "fp64" else "tf32_sustained")] = rate * flop / 1e12 / peak
+        row[key + "_frac_of_" + ("f64_peak" if prec == "fp64" else "bf16_sustained")] = rate * flop / 1e12 / peak
     s64, i64 = gp.score_pool(pool[:1 << 18], acq, 8, precision="fp64")
     sr, ir = gp.score_pool(pool[:1 << 18], acq, 8, precision="tf32+refine")
     row["refine_selection_matches_fp64"] = bool(torch.equal(ir, i64))

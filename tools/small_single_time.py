@@ -1,5 +1,6 @@
+"""One small problem (n=256, d=10) alone: fit iteration and scoring latency (development aid)."""
 import sys, os, json
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bbo_b200 as B
 from bbo_b200.benchmarks import Branin2D, Ackley, make_observations
